@@ -1,0 +1,176 @@
+"""Pin the CPU oracle against vectors produced by the reference itself (tests/golden/make_golden.py)
+and against the reference's own known-answer tests.  CPU only."""
+import pytest
+import torch
+
+from oracle import neuradar_oracle as O
+
+
+def params_from_golden(g, prefix=""):
+    main = O.GridParams(g[prefix + "main_table"], O.level_scalings(16, 16, 1024), 10)
+    fld = O.FieldParams(
+        grid=main,
+        geo_w=[g[f"{prefix}geo_w{k}"] for k in range(2)],
+        geo_b=[g[f"{prefix}geo_b{k}"] for k in range(2)],
+        feat_w=[g[f"{prefix}feat_w{k}"] for k in range(3)],
+        feat_b=[g[f"{prefix}feat_b{k}"] for k in range(3)],
+        beta=g[prefix + "beta"],
+    )
+    props = [
+        O.ProposalParams(O.GridParams(g[f"{prefix}prop{i}_table"], O.level_scalings(6, 128, 4096), 10), g[f"{prefix}prop{i}_w"])
+        for i in range(2)
+    ]
+    return fld, props
+
+
+def test_level_scalings(golden):
+    g = golden("hash")
+    assert torch.equal(O.level_scalings(16, 16, 1024), g["scalings_A"])
+    assert torch.equal(O.level_scalings(8, 32, 8192), g["scalings_B"])
+    assert torch.equal(O.level_scalings(6, 128, 4096), g["scalings_P"])
+    assert torch.equal(O.level_scalings(4, 64, 1024), g["scalings_actor"])
+    assert g["scalings_B"][-1].item() == 8191.0  # SURVEY.md section 0, trap 2
+    assert g["scalings_A"].tolist() == [16, 21, 27, 36, 48, 64, 84, 111, 147, 194, 256, 337, 445, 588, 776, 1024]
+
+
+def test_hash_known_answers(golden):
+    g = golden("hash")
+    coords = g["kat_coords"][:, None, :].expand(-1, 16, -1)
+    got = O.hash_coords(coords, 19)
+    assert got.dtype == torch.int64 and torch.equal(got, g["kat_hash"])
+    # values recorded in SURVEY.md 8c (level 0 / level 15)
+    want = {(0, 0, 0): (0, 7864320), (1, 0, 0): (1, 7864321), (0, 1, 0): (489905, 8354225), (0, 0, 1): (153493, 8017813),
+            (1, 1, 1): (339493, 8203813), (15, 16, 17): (19450, 7883770), (1023, 1024, 1): (299114, 8163434),
+            (-1, -2, 3): (128478, 7992798)}
+    for row, c in enumerate(g["kat_coords"].tolist()):
+        if tuple(c) in want:
+            assert (got[row, 0].item(), got[row, 15].item()) == want[tuple(c)]
+    # uint32 wrap-around formulation used by the CUDA kernels is bit-identical
+    c = g["kat_coords"].to(torch.int64) & 0xFFFFFFFF
+    h32 = (c[:, 0] ^ ((c[:, 1] * O.PRIME_Y) & 0xFFFFFFFF) ^ ((c[:, 2] * O.PRIME_Z) & 0xFFFFFFFF)) & ((1 << 19) - 1)
+    assert torch.equal(h32, g["kat_hash"][:, 0])
+
+
+@pytest.mark.parametrize("F", [1, 2, 4])
+def test_hash_encode_forward_backward(golden, F):
+    g = golden("hash")
+    table = g[f"F{F}_table"].clone().requires_grad_(True)
+    x = g["x"].clone().requires_grad_(True)
+    y = O.hash_encode(x, table, g["scalings_A"], 10)
+    assert torch.equal(y, g[f"F{F}_y"])
+    (y * g[f"F{F}_dy"]).sum().backward()
+    torch.testing.assert_close(table.grad, g[f"F{F}_dtable"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(x.grad, g[f"F{F}_dx"], rtol=1e-5, atol=1e-5)
+
+
+def test_reference_known_answer_tests(golden):
+    g = golden("kats")
+    # reference tests/cameras/test_rays.py:11-30
+    assert torch.equal(g["frustum_positions"], torch.tensor([1.0, 3.5, 1.0]).expand(5, 3))
+    # SURVEY.md 8c vectors
+    w, T = O.alpha_weights(g["alpha_in"][..., 0], eps=1e-7)
+    assert torch.equal(w, g["alpha_w"][..., 0]) and torch.equal(T, g["alpha_T"][..., 0])
+    torch.testing.assert_close(w[0], torch.tensor([0.1, 0.45000005, 0.40500015, 0.0090000136]), rtol=1e-6, atol=0)
+    torch.testing.assert_close(g["gw_kat"].flatten(), torch.tensor([0.39346933, 0.3834005, 0.08779488, 0.12859733]), rtol=1e-6, atol=0)
+    # reference tests/utils/test_math.py:8-16: SH basis is orthonormal over the sphere
+    gen = torch.Generator().manual_seed(0)
+    d = torch.randn((200000, 3), generator=gen)
+    d = d / d.norm(dim=-1, keepdim=True)
+    sh = O.sh16(d)
+    gram = 4 * torch.pi * (sh.T @ sh) / d.shape[0]
+    torch.testing.assert_close(gram, torch.eye(16), rtol=0, atol=3e-2)
+
+
+def test_weights_and_renderers(golden):
+    g = golden("kats")
+    w, T = O.alpha_weights(g["alpha2_in"][..., 0], eps=1e-7)
+    assert torch.equal(w, g["alpha2_w"][..., 0]) and torch.equal(T, g["alpha2_T"][..., 0])
+    w0, _ = O.alpha_weights(g["alpha2_in"][..., 0], eps=0.0)  # nerfacc contract vs in-tree twin
+    torch.testing.assert_close(w0, w, rtol=1e-4, atol=1e-6)
+    bins = g["gw_bins"]
+    dens = g["gw_dens"].clone().requires_grad_(True)
+    gw = O.density_weights(dens, (bins[:, 1:] - bins[:, :-1])[..., None])
+    assert torch.equal(gw, g["gw_w"])
+    (gw * g["gw_dw"]).sum().backward()
+    torch.testing.assert_close(dens.grad, g["gw_ddens"], rtol=1e-6, atol=0, equal_nan=True)
+    starts, ends = bins[:, :-1], bins[:, 1:]
+    assert torch.equal(torch.sum(g["rend_feats"] * g["rend_w"], dim=-2), g["rend_feature"])
+    assert torch.equal(O.expected_depth(g["rend_w"], starts, ends), g["rend_depth_expected"])
+    assert torch.equal(O.median_depth(g["rend_w"] * 3, starts, ends), g["rend_depth_median"])
+    assert torch.equal(O.sh16((g["sh_dirs"] + 1.0) / 2.0), g["sh_out"])
+    assert torch.equal(O.sh16(g["sh_dirs"]), g["sh_enc"])
+
+
+@pytest.mark.parametrize("tag,n", [("geo", 2), ("feat", 3), ("lidar", 3), ("radar", 3)])
+def test_mlp(golden, tag, n):
+    g = golden("kats")
+    ws = [g[f"mlp_{tag}_w{k}"].clone().requires_grad_(True) for k in range(n)]
+    bs = [g[f"mlp_{tag}_b{k}"].clone().requires_grad_(True) for k in range(n)]
+    x = g[f"mlp_{tag}_x"].clone().requires_grad_(True)
+    y = O.mlp(x, ws, bs)
+    assert torch.equal(y, g[f"mlp_{tag}_y"])
+    (y * g[f"mlp_{tag}_dy"]).sum().backward()
+    torch.testing.assert_close(x.grad, g[f"mlp_{tag}_dx"], rtol=1e-6, atol=1e-7)
+    for k in range(n):
+        torch.testing.assert_close(ws[k].grad, g[f"mlp_{tag}_dw{k}"], rtol=1e-6, atol=1e-7)
+        torch.testing.assert_close(bs[k].grad, g[f"mlp_{tag}_db{k}"], rtol=1e-6, atol=1e-7)
+
+
+def test_pdf_sampler_known_answer(golden):
+    g = golden("samplers")
+    bins, inds, cdf, u = O.pdf_sample(g["kat_w"][..., 0], g["kat_in_sbins"], 4, None)
+    assert torch.equal(bins, g["kat_sbins"])
+    torch.testing.assert_close(bins[0], torch.tensor([0.33514851, 0.40910226, 0.45324191, 0.49738157, 0.58283591]), rtol=1e-6, atol=0)
+    torch.testing.assert_close(bins[1], torch.tensor([0.1, 0.3, 0.5, 0.7, 0.9]), rtol=1e-6, atol=0)
+    torch.testing.assert_close(2.0 + 4.0 * bins[0, :4], torch.tensor([3.3405938, 3.6364093, 3.8129675, 3.9895263]), rtol=1e-6, atol=0)
+    assert torch.equal(2.0 + (6.0 - 2.0) * bins[:, :4], g["kat_starts"]) or torch.allclose(
+        bins[:, :4] * 6.0 + (1 - bins[:, :4]) * 2.0, g["kat_starts"], rtol=1e-6
+    )
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_samplers(golden, mode):
+    g = golden("samplers")
+    j0 = g[f"{mode}_j0"] if mode == "train" else None
+    j1 = g[f"{mode}_j1"] if mode == "train" else None
+    sb0, eb0, sp = O.spaced_bins(g["nears"], g["fars"], 64, j0)
+    assert torch.equal(sb0.expand(96, -1), g[f"{mode}_sbins0"])
+    assert torch.equal(eb0, g[f"{mode}_ebins0"])
+    sb1, inds, cdf, u = O.pdf_sample(g[f"{mode}_w"][..., 0], sb0.expand(96, -1), 48, j1)
+    assert torch.equal(sb1, g[f"{mode}_sbins1"])
+    assert torch.equal(sp.to_euclidean(sb1), g[f"{mode}_ebins1"])
+    assert inds.dtype == torch.int64 and inds.min() >= 1 and inds.max() <= 64
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_whole_path(golden, mode):
+    g = golden("path")
+    fld, props = params_from_golden(g)
+    leaves = [fld.grid.table, *fld.geo_w, *fld.geo_b, *fld.feat_w, *fld.feat_b, fld.beta] + [p.grid.table for p in props] + [p.decoder_w for p in props]
+    for t in leaves:
+        t.requires_grad_(True)
+    cfg = O.PathConfig(num_proposal_samples=(64, 48), num_nerf_samples=48)
+    jit = [g[f"{mode}_jitter{i}"] for i in range(3)] if mode == "train" else None
+    out = O.nff_forward(fld, props, g["origins"], g["directions"], g["pixel_area"], g["nears"], g["fars"], cfg, jit, composite_eps=1e-7)
+    pre = mode + "_"
+    for i in range(2):
+        assert torch.equal(out.sbins_list[i], g[f"{pre}sbins{i}"])
+        assert torch.equal(out.ebins_list[i], g[f"{pre}ebins{i}"])
+        torch.testing.assert_close(out.weights_list[i], g[f"{pre}prop_w{i}"], rtol=1e-6, atol=1e-9)
+    assert torch.equal(out.sbins_list[2], g[f"{pre}sbins2"][:, :-1])
+    assert torch.equal(out.ebins_list[2], g[f"{pre}ebins2"][:, :-1])
+    torch.testing.assert_close(out.features, g[f"{pre}features"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(out.depth, g[f"{pre}depth"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(out.accumulation, g[f"{pre}accumulation"], rtol=1e-6, atol=1e-8)
+    torch.testing.assert_close(out.weights_list[2], g[f"{pre}weights"], rtol=1e-6, atol=1e-9)
+    loss = O.bench_loss(out)
+    torch.testing.assert_close(loss, g[f"{pre}loss"], rtol=1e-6, atol=0)
+    if mode == "train":
+        loss.backward()
+        names = (["d_main_table"] + [f"d_geo_w{k}" for k in range(2)] + [f"d_geo_b{k}" for k in range(2)]
+                 + [f"d_feat_w{k}" for k in range(3)] + [f"d_feat_b{k}" for k in range(3)] + ["d_beta"]
+                 + [f"d_prop{i}_table" for i in range(2)] + [f"d_prop{i}_w" for i in range(2)])
+        for t, n in zip(leaves, names):
+            ref = g[pre + n]
+            scale = ref.abs().max().item() + 1e-30
+            assert (t.grad - ref).abs().max().item() <= 1e-5 * scale, n
