@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the NeuRadar per-ray hot path (BASELINE.json: train-step rays/sec at 1/2/4/8 B200).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+
+A step = one fwd+bwd pass of the hot path (proposal sampling -> hash encode -> MLPs -> compositing, loss of
+SURVEY.md 8d, gradients of every hash table and MLP) over one batch of synthetic rays; for N > 1 each rank owns
+its own rays (weak scaling, 65536 rays per GPU) and the step ends with ONE all-reduce of the flat gradient arena.
+Workload at N=1 = BASELINE.json configs[1]: 65536 mixed camera/lidar/radar rays, 16-level 2^19 main grid, 48
+samples per ray, proposal rounds of 64 and 48 samples on the 6-level 2^20 grid.  Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "train_step_rays_per_sec"
+UNIT = "rays/s"
+RAYS_PER_GPU = 65536
+PROP_SAMPLES = (64, 48)
+NERF_SAMPLES = 48
+WORKLOAD = ("config2: 65536 mixed camera/lidar/radar rays per GPU, main grid L16/F2/T2^19 (res 16..1024), "
+            "proposals (64,48) on L6/F1/T2^20, 48 samples/ray, fwd+bwd")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            p = json.load(fh)
+        return {"hbm_gbs": p["hbm_gbs"], "tflops": p.get("bf16_tflops_sustained", p.get("bf16_tflops")), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """Samples SM clocks and throttle reasons with NVML while the timed region runs."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                mask = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+        return False
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42):
+    """fwd+bwd of the reference algorithm (CPU oracle port, fp32 torch ops) on `num_rays` rays of the workload."""
+    from oracle import neuradar_oracle as O
+    from tests.parity_utils import scaled_pixel_area, synthetic_rays
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(seed)
+    main = O.GridParams(((torch.rand((16 << 19, 2)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(16, 16, 1024), 19)
+    lin = torch.nn.Linear
+
+    def wb(i, o):
+        layer = lin(i, o)
+        return layer.weight.detach().requires_grad_(True), layer.bias.detach().requires_grad_(True)
+
+    g0, g1 = wb(32, 32), wb(32, 33)
+    f0, f1, f2 = wb(48, 32), wb(32, 32), wb(32, 32)
+    fld = O.FieldParams(main, [g0[0], g1[0]], [g0[1], g1[1]], [f0[0], f1[0], f2[0]], [f0[1], f1[1], f2[1]],
+                        torch.full((1,), 20.0, requires_grad=True))
+    prop = O.ProposalParams(
+        O.GridParams(((torch.rand((6 << 20, 1)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(6, 128, 4096), 20),
+        lin(6, 1, bias=False).weight.detach().requires_grad_(True),
+    )
+    rays = synthetic_rays(num_rays, seed=seed)
+    pa = scaled_pixel_area(rays)
+    cfg = O.PathConfig(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES)
+    leaves = [main.table, *fld.geo_w, *fld.geo_b, *fld.feat_w, *fld.feat_b, fld.beta, prop.grid.table, prop.decoder_w]
+
+    def step():
+        for t in leaves:
+            t.grad = None
+        jit = [torch.rand((num_rays, PROP_SAMPLES[0] + 1)), torch.rand((num_rays, 1)), torch.rand((num_rays, 1))]
+        out = O.nff_forward(fld, [prop, prop], rays["origins"], rays["directions"], pa, rays["nears"], rays["fars"], cfg, jit)
+        O.bench_loss(out).backward()
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return num_rays / dt, dt * 1e3, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    sample = 4096
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    value, ms, cores = cpu_reference_run(sample, steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "reference algorithm on the host CPU; the reference is pure Python and "
+                   "cannot travel to the GPU box, so this is the oracle port of its torch path"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} of the 65536 rays per step, {steps} timed fwd+bwd steps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+ALGO = {
+    # algorithmic bytes per sample of one launch (8 corners x L x F x 4 B, gathers/scatters counted once)
+    "nrb_hash_fwd:L16F2T19": ("hbm", 8 * 16 * 2 * 4), "nrb_hash_bwd:L16F2T19": ("hbm", 8 * 16 * 2 * 4),
+    "nrb_proposal_fwd": ("hbm", 8 * 6 * 1 * 4), "nrb_proposal_bwd": ("hbm", 8 * 6 * 1 * 4),
+}
+MLP_FLOP_FWD = {"geo": 2 * (32 * 32 + 32 * 33), "feature": 2 * (48 * 32 + 32 * 32 + 32 * 32)}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    import neuradar_b200 as nb
+    from neuradar_b200 import _lib
+    from neuradar_b200.dist import GradArena
+    from tests.parity_utils import build_hot_path, synthetic_rays
+
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    n = args.rays
+    model = build_hot_path(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES, seed=42, device=dev)
+    model.train()
+    used = [p for name, p in model.named_parameters() if not name.startswith("proposal_fields.0")]
+    arena = GradArena(used)
+    rays = synthetic_rays(n, seed=42 + rank)  # each rank draws its own rays (train.py:104 seeds seed+rank)
+    keys = ["origins", "directions", "pixel_area", "nears", "fars", "times", "is_lidar", "is_radar"]
+    host = {k: rays[k].pin_memory() for k in keys}
+    resident = {k: rays[k].to(dev) for k in keys}
+    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
+
+    def bundle(src):
+        return nb.RayBundle(origins=src["origins"].clone(), directions=src["directions"].clone(),
+                            pixel_area=src["pixel_area"].clone(), nears=src["nears"].clone(), fars=src["fars"].clone(),
+                            times=src["times"], metadata={"is_lidar": src["is_lidar"], "is_radar": src["is_radar"]})
+
+    def step(src):
+        arena.zero()
+        out = model(bundle(src))
+        loss = nb.bench_loss(out)
+        loss.backward()
+        arena.all_reduce()
+        return loss
+
+    def step_e2e():
+        dev_rays = {k: host[k].to(dev, non_blocking=True) for k in keys}
+        return step(dev_rays).item()  # device -> host read of the step's loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()) / steps
+
+    for _ in range(args.warmup):
+        step(resident)
+    launches0 = _lib.launch_count()
+    with ClockSampler(local_rank) as clocks:
+        ms = timed(lambda: step(resident), args.steps)
+    launches = _lib.launch_count() - launches0
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    # per-kernel durations from CUDA events on the launching stream (separate pass: the events add launch gaps)
+    _lib.TIMER = _lib.KernelTimer()
+    for _ in range(max(3, min(args.steps, 10))):
+        step(resident)
+    kernels = _lib.TIMER.summary()
+    _lib.TIMER = None
+
+    peaks = load_peaks()
+    total_rays = n * world
+    samples = {"nrb_hash_fwd:L16F2T19": n * NERF_SAMPLES, "nrb_hash_bwd:L16F2T19": n * NERF_SAMPLES}
+    per_step = {}
+    for name, (count, mean_ms) in kernels.items():
+        per_step[name] = {"launches_per_step": count / max(3, min(args.steps, 10)), "mean_ms": mean_ms}
+    # dominant memory-bound kernel: the main-field hash gather / scatter
+    cand = {k: v for k, v in kernels.items() if k in ("nrb_hash_fwd:L16F2T19", "nrb_hash_bwd:L16F2T19")}
+    roofline = None
+    if cand:
+        name = max(cand, key=lambda k: cand[k][1])
+        bytes_per_launch = samples[name] * ALGO[name][1]
+        achieved = bytes_per_launch / (cand[name][1] * 1e-3) / 1e9
+        roofline = {"kernel": name, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"],
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": cand[name][1]}
+
+    line = {
+        "metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": n, "global_rays": total_rays,
+                   "parallelism": f"ray-sharded dp{world}, one all-reduce of a {arena.nbytes / 2**20:.0f} MiB gradient arena",
+                   "l2": "per-step working set (saved activations + gradient arena, > 1 GB) exceeds the 126 MB L2; "
+                         "no explicit flush", "optimizer": "not part of the path (SURVEY.md 8f next-2)"},
+        "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "kernels": per_step,
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            v, cms, cores = cpu_reference_run(4096, 2, 1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "4096 of the 65536 rays per step, 2 timed fwd+bwd steps of the oracle"}
+        print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: neuradar_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    if world > 1:
+        import torch.distributed as dist
+
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend="nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    try:
+        run_b200(args, rank, world, local_rank)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,191 @@
+/*
+ * neuradar_b200.h - C ABI of libneuradar_b200.so: the NeuRadar per-ray neural-field hot path on B200 (sm_100a).
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer to a contiguous row-major fp32 array unless stated otherwise;
+ *   - the caller owns and pre-allocates every buffer; no entry point allocates or synchronises;
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); distinct streams may be used concurrently;
+ *   - return value: 0 on success, a negative NRB_ERR_* code for argument errors (nothing is launched), or the
+ *     positive cudaError_t of the failed launch.  nrb_last_error_string() describes the last failure of the
+ *     calling thread.
+ *   - there is no CPU fallback: on a machine without an sm_100 device every launch fails with a CUDA error.
+ *
+ * The reference (mrafidashti/neuradar, a nerfstudio fork) has no native code; each entry point below replaces a
+ * call site of its torch / tiny-cuda-nn / nerfacc path.  Citations are file:line in the reference checkout.
+ */
+#ifndef NEURADAR_B200_H
+#define NEURADAR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRB_VERSION 100 /* major*10000 + minor*100 + patch */
+
+#define NRB_OK 0
+#define NRB_ERR_BAD_ARG (-1)     /* null pointer, non-positive or out-of-range dimension */
+#define NRB_ERR_ALIGNMENT (-2)   /* a vector-accessed pointer is not 16-byte aligned */
+#define NRB_ERR_UNSUPPORTED (-3) /* configuration outside what the kernels were built for */
+
+#define NRB_MAX_LEVELS 16
+#define NRB_MAX_MLP_LAYERS 4
+#define NRB_MAX_MLP_WIDTH 64
+#define NRB_MAX_SAMPLES 256 /* samples per ray handled by the warp-per-ray kernels */
+
+typedef void* nrb_stream_t; /* cudaStream_t */
+
+/* One multiresolution hash grid = HashEncoding (nerfstudio/field_components/encodings.py:311-384).
+ * `table` is the `hash_table` parameter [num_levels * 2^log2_hashmap_size, features_per_level];
+ * `scalings` are the per-level resolutions of the `scalings` buffer (encodings.py:350), by value. */
+typedef struct {
+  const float* table;
+  float scalings[NRB_MAX_LEVELS];
+  int32_t num_levels;
+  int32_t features_per_level; /* 1, 2 or 4 */
+  int32_t log2_hashmap_size;  /* <= 24 */
+} nrb_grid_t;
+
+/* Per-ray inputs = the RayBundle fields the path reads (nerfstudio/cameras/rays.py:251-271), un-broadcast. */
+typedef struct {
+  const float* origins;    /* [N,3] */
+  const float* directions; /* [N,3] */
+  const float* pixel_area; /* [N]   */
+  const float* nears;      /* [N]   */
+  const float* fars;       /* [N]   */
+  int64_t num_rays;
+} nrb_rays_t;
+
+/* Sample intervals along rays = Frustums.starts / Frustums.ends (nerfstudio/cameras/rays.py:41-44), [N, S] each
+ * with a common row stride.  Samples cut from S+1 shared bin edges (what every sampler on the path produces,
+ * ray_samplers.py:122-129,368-374) are passed as starts = bins, ends = bins + 1, row_stride = S + 1. */
+typedef struct {
+  const float* starts;
+  const float* ends;
+  int64_t row_stride;
+  int32_t num_samples;
+} nrb_intervals_t;
+
+/* Linear+ReLU chain = MLP.pytorch_fwd (nerfstudio/field_components/mlp.py:142-178).
+ * weights[i] is layers.i.weight [dims[i+1], dims[i]], biases[i] is layers.i.bias [dims[i+1]] or NULL. */
+typedef struct {
+  const float* weights[NRB_MAX_MLP_LAYERS];
+  const float* biases[NRB_MAX_MLP_LAYERS];
+  int32_t dims[NRB_MAX_MLP_LAYERS + 1];
+  int32_t num_layers;
+} nrb_mlp_t;
+
+/* Gradient sinks matching nrb_mlp_t; every buffer is ACCUMULATED into (caller zeroes). */
+typedef struct {
+  float* weights[NRB_MAX_MLP_LAYERS];
+  float* biases[NRB_MAX_MLP_LAYERS];
+} nrb_mlp_grad_t;
+
+/* Power-transform spacing of PowerSampler (nerfstudio/model_components/ray_samplers.py:838-852,
+ * nerfstudio/utils/math.py:541-580): spacing_fn(x) = power_fn(x*scaling, lambda). */
+typedef struct {
+  float lambda;
+  float scaling;
+} nrb_spacing_t;
+
+int nrb_version(void);
+const char* nrb_last_error_string(void);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t nrb_launch_count(void);
+
+/* ---- hash grid: HashEncoding.pytorch_fwd, encodings.py:425-466 (replaces the tcnn.Encoding call, :468-470) ----
+ * x [M,3] in grid units [0,1]; out [M, L*F].  When `std` [M] is non-NULL each level is additionally multiplied by
+ * 1/max(1, 2*scalings[l]*std) = NeuRADHashEncoding._rescale_grid_features (neurad_encoding.py:309-316). */
+int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float* std, float* out, int64_t M, nrb_stream_t stream);
+/* Table rows of the 8 cell corners, idx [M, L, 8] int64 in the corner order of encodings.py:436-443
+ * (HashEncoding.hash_fn, encodings.py:406-423).  Parity/debug entry: bit-exact with the reference. */
+int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t* idx, int64_t M, nrb_stream_t stream);
+/* Backward of nrb_hash_fwd: dtable [L*T, F] += scatter(dy [M, L*F]);  dx [M,3] (optional, may be NULL) is
+ * OVERWRITTEN with the gradient through the in-cell offsets (floor/ceil have zero gradient). */
+int nrb_hash_bwd(const nrb_grid_t* grid, const float* x, const float* std, const float* dy, float* dtable, float* dx,
+                 int64_t M, nrb_stream_t stream);
+
+/* ---- sample gaussians + contraction: Frustums.get_fast_isotropic_gaussian(1) (cameras/rays.py:109-124) followed by
+ * ScaledSceneContraction(order=inf, scale) on GaussiansStd (field_components/spatial_distortions.py:103-113,132-136).
+ * x [N*S, 3] contracted means in [0,1]^3, std [N*S] contracted standard deviations. */
+int nrb_frustum_gaussians(const nrb_rays_t* rays, const nrb_intervals_t* iv, float scale, float* x, float* std,
+                          nrb_stream_t stream);
+
+/* ---- tiny MLP: MLP.pytorch_fwd (mlp.py:159-178; replaces tcnn.Network, mlp.py:109-113) ----
+ * x [M, dims[0]] -> y [M, dims[L]].  `hidden` (optional) receives the post-ReLU activations of the L-1 hidden
+ * layers, feature-major: layer i at hidden + M * sum(dims[1..i]) laid out [dims[i+1], M]; needed by nrb_mlp_bwd. */
+int nrb_mlp_fwd(const nrb_mlp_t* mlp, const float* x, float* y, float* hidden, int64_t M, nrb_stream_t stream);
+int nrb_mlp_bwd(const nrb_mlp_t* mlp, const float* x, const float* hidden, const float* dy, float* dx,
+                const nrb_mlp_grad_t* grads, int64_t M, nrb_stream_t stream);
+
+/* ---- degree-4 real spherical harmonics of (d+1)/2: SHEncoding.pytorch_fwd on get_normalized_directions
+ * (encodings.py:797-805, utils/math.py:31-94, fields/base_field.py:136-142).  dirs [M,3] -> out [M,16]. */
+int nrb_sh16(const float* dirs, float* out, int64_t M, int32_t normalize_to_unit_cube, nrb_stream_t stream);
+
+/* ---- samplers ----
+ * SpacedSampler/PowerSampler.generate_ray_samples (ray_samplers.py:80-132).  base_bins [S+1] = linspace(0,1,S+1);
+ * jitter is the torch.rand draw: [N] (jitter_per_bin=0, single_jitter) or [N, S+1] (jitter_per_bin=1), or NULL in
+ * eval mode.  Outputs: spacing bins sbins [N, S+1] and euclidean bins ebins [N, S+1]. */
+int nrb_spaced_bins(const nrb_rays_t* rays, nrb_spacing_t spacing, const float* base_bins, const float* jitter,
+                    int32_t jitter_per_bin, int32_t S, float* sbins, float* ebins, nrb_stream_t stream);
+/* PDFSampler.generate_ray_samples with include_original=False (ray_samplers.py:280-376): inverse-CDF importance
+ * sampling of S_out+1 new bin edges from S_in weighted bins.  weights [N, S_in]; sbins_in [N, S_in+1];
+ * u_base [S_out+1] = linspace(0, 1-1/nb, nb); jitter [N] (training, single_jitter) or NULL (eval: +1/(2nb)).
+ * Outputs sbins_out / ebins_out [N, S_out+1]; optional inds [N, S_out+1] int64 (= torch.searchsorted(cdf, u,
+ * side="right"), ray_samplers.py:349) and cdf [N, S_in+1] for stage-level parity checks. */
+int nrb_pdf_sample(const nrb_rays_t* rays, nrb_spacing_t spacing, const float* weights, const float* sbins_in,
+                   int32_t S_in, const float* u_base, const float* jitter, int32_t S_out, float histogram_padding,
+                   float eps, float* sbins_out, float* ebins_out, int64_t* inds, float* cdf, nrb_stream_t stream);
+
+/* ---- compositing ----
+ * RaySamples.get_weights (cameras/rays.py:188-210): weights [N,S] from densities [N,S], deltas = ends - starts. */
+int nrb_density_weights_fwd(const float* densities, const nrb_intervals_t* iv, int64_t N, float* weights,
+                            nrb_stream_t stream);
+int nrb_density_weights_bwd(const float* densities, const nrb_intervals_t* iv, const float* dweights, int64_t N,
+                            float* ddensities, nrb_stream_t stream);
+/* Alpha compositing tail of NeuRadarModel.get_nff_outputs (models/neuradar.py:504-517): replaces
+ * nerfacc.render_weight_from_alpha (:1016), AccumulationRenderer, FeatureRenderer (renderers.py:59-90,322-350)
+ * and render_depth_simple (models/neurad.py:721-728).
+ *   T_i = prod_{j<i}(1 - alpha_j + trans_eps); w_i = alpha_i T_i; acc = sum w;
+ *   sky_sample != 0: w_{S-1} += 1 - acc before the feature sum, and depth excludes sample S-1;
+ *   features[N,C] = sum_s w f; depth[N] = sum_s w (start+end)/2.
+ * alphas [N,S], feats [N,S,C] (C multiple of 4, <= 64), iv the sample intervals; outputs weights [N,S] (after the sky
+ * fix-up), features [N,C], depth [N], accumulation [N], transmittance [N,S] (T_i); each output may be NULL.
+ * trans_eps = 0 (nerfacc) or 1e-7 (cameras/rays.py:242). */
+int nrb_alpha_composite_fwd(const float* alphas, const float* feats, const nrb_intervals_t* iv, int64_t N, int32_t C,
+                            float trans_eps, int32_t sky_sample, float* weights, float* features, float* depth,
+                            float* accumulation, float* transmittance, nrb_stream_t stream);
+/* Backward: upstream dweights [N,S] (may be NULL), dfeatures [N,C], ddepth [N], daccumulation [N] (each may be
+ * NULL) -> dalphas [N,S], dfeats [N,S,C]. */
+int nrb_alpha_composite_bwd(const float* alphas, const float* feats, const nrb_intervals_t* iv, int64_t N, int32_t C,
+                            float trans_eps, int32_t sky_sample, const float* dweights, const float* dfeatures,
+                            const float* ddepth, const float* daccumulation, float* dalphas, float* dfeats,
+                            nrb_stream_t stream);
+
+/* nerfacc.accumulate_along_rays on dense samples (call sites models/neurad.py:728, renderers.py:85,349,412):
+ * out [N,C] = sum_s weights[N,S] * values[N,S,C]; values == NULL gives out [N] = sum_s weights. */
+int nrb_accumulate_fwd(const float* weights, const float* values, int64_t N, int32_t S, int32_t C, float* out,
+                       nrb_stream_t stream);
+int nrb_accumulate_bwd(const float* weights, const float* values, const float* dout, int64_t N, int32_t S, int32_t C,
+                       float* dweights, float* dvalues, nrb_stream_t stream);
+
+/* ---- fused proposal round: NeuRADProposalField.get_density + RaySamples.get_weights
+ * (fields/neurad_field.py:208-213, cameras/rays.py:188-210) in one kernel, one warp per ray:
+ * gaussians -> contraction -> hash encode -> level weights -> Linear(L*F, 1, bias=False) -> trunc_exp -> weights.
+ * decoder_w [L*F].  Outputs: density [N,S], weights [N,S]; when `saved_feats` [N,S,L*F] and `saved_pre` [N,S]
+ * are non-NULL the rescaled features and the pre-activation are kept for the backward pass. */
+int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w, float static_scale,
+                     const nrb_intervals_t* iv, float* density, float* weights, float* saved_feats, float* saved_pre,
+                     nrb_stream_t stream);
+/* Backward of the fused round given dweights [N,S] and/or ddensity [N,S] (either may be NULL):
+ * dtable += ..., ddecoder_w [L*F] += ... */
+int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w, float static_scale,
+                     const nrb_intervals_t* iv, const float* saved_feats, const float* saved_pre,
+                     const float* dweights, const float* ddensity, float* dtable, float* ddecoder_w,
+                     nrb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NEURADAR_B200_H */

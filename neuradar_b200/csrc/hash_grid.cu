@@ -1,0 +1,235 @@
+// Multiresolution hash grid: forward gather, index dump, backward scatter, and the sample-gaussian producer.
+// Semantics: HashEncoding.pytorch_fwd / hash_fn (nerfstudio/field_components/encodings.py:406-466) and
+// NeuRADHashEncoding._rescale_grid_features (nerfstudio/field_components/neurad_encoding.py:309-316).
+//
+// Work decomposition: one thread per (point, level) pair with the level index fastest.  The 2^19..2^22-row tables
+// are hit at random, so there is nothing to coalesce on the gather side; what can be coalesced is the [M, L*F]
+// feature matrix, and with the level fastest a warp writes (reads, in the backward pass) one contiguous
+// 32*F*4-byte span of it.  Each thread issues its 8 independent F-wide vector gathers before touching any of them.
+#include "common.cuh"
+
+namespace nrb {
+
+struct GridDev {
+  const float* table;
+  float scalings[NRB_MAX_LEVELS];
+  int num_levels;
+  int log2_size;
+};
+
+static GridDev to_dev(const nrb_grid_t* g) {
+  GridDev d;
+  d.table = g->table;
+  for (int i = 0; i < NRB_MAX_LEVELS; ++i) d.scalings[i] = g->scalings[i];
+  d.num_levels = g->num_levels;
+  d.log2_size = g->log2_hashmap_size;
+  return d;
+}
+
+template <int F>
+__global__ void __launch_bounds__(256) hash_fwd_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
+                                                       const float* __restrict__ std, float* __restrict__ out,
+                                                       int64_t total) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int64_t m = gid / g.num_levels;
+  const int l = static_cast<int>(gid - m * g.num_levels);
+  const float scal = g.scalings[l];
+  const Cell c = locate_cell(__ldg(x + 3 * m), __ldg(x + 3 * m + 1), __ldg(x + 3 * m + 2), scal,
+                             (1u << g.log2_size) - 1u);
+  const float* base = g.table + (static_cast<size_t>(l) << g.log2_size) * F;
+  float v[F];
+  interpolate<F>(base, c, v);
+  if (std != nullptr) {
+    const float w = level_weight(scal, __ldg(std + m));
+#pragma unroll
+    for (int j = 0; j < F; ++j) v[j] *= w;
+  }
+  using V = typename Feat<F>::type;
+  V o;
+  if constexpr (F == 1) {
+    o = v[0];
+  } else if constexpr (F == 2) {
+    o = make_float2(v[0], v[1]);
+  } else {
+    o = make_float4(v[0], v[1], v[2], v[3]);
+  }
+  reinterpret_cast<V*>(out)[gid] = o;
+}
+
+__global__ void __launch_bounds__(256) hash_indices_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
+                                                           int64_t* __restrict__ idx, int64_t total) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int64_t m = gid / g.num_levels;
+  const int l = static_cast<int>(gid - m * g.num_levels);
+  const Cell c = locate_cell(x[3 * m], x[3 * m + 1], x[3 * m + 2], g.scalings[l], (1u << g.log2_size) - 1u);
+  const int64_t off = static_cast<int64_t>(l) << g.log2_size;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) idx[gid * 8 + k] = off + c.row[k];
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_row(float* __restrict__ base, uint32_t row, const float g[F], float w) {
+  float* p = base + static_cast<size_t>(row) * F;
+  if constexpr (F == 1) {
+    atomicAdd(p, g[0] * w);
+  } else if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(g[0] * w, g[1] * w));
+  } else {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(g[0] * w, g[1] * w, g[2] * w, g[3] * w));
+  }
+}
+
+template <int F, bool kNeedDx>
+__global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
+                                                       const float* __restrict__ std, const float* __restrict__ dy,
+                                                       float* __restrict__ dtable, float* __restrict__ dx,
+                                                       int64_t total) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int64_t m = gid / g.num_levels;
+  const int l = static_cast<int>(gid - m * g.num_levels);
+  const float scal = g.scalings[l];
+  const Cell c = locate_cell(__ldg(x + 3 * m), __ldg(x + 3 * m + 1), __ldg(x + 3 * m + 2), scal,
+                             (1u << g.log2_size) - 1u);
+  using V = typename Feat<F>::type;
+  const V gv = __ldg(reinterpret_cast<const V*>(dy) + gid);
+  float gr[F];
+  if constexpr (F == 1) {
+    gr[0] = gv;
+  } else if constexpr (F == 2) {
+    gr[0] = gv.x;
+    gr[1] = gv.y;
+  } else {
+    gr[0] = gv.x;
+    gr[1] = gv.y;
+    gr[2] = gv.z;
+    gr[3] = gv.w;
+  }
+  if (std != nullptr) {
+    const float lw = level_weight(scal, __ldg(std + m));
+#pragma unroll
+    for (int j = 0; j < F; ++j) gr[j] *= lw;
+  }
+  const size_t level_off = (static_cast<size_t>(l) << g.log2_size) * F;
+  if constexpr (kNeedDx) {
+    // d out / d offset needs the corner features themselves.
+    float f[8][F];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) load_row<F>(g.table + level_off, c.row[k], f[k]);
+    const float ax = c.ox, bx = 1.0f - c.ox, ay = c.oy, by = 1.0f - c.oy, az = c.oz, bz = 1.0f - c.oz;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      const float f03 = f[0][j] * ax + f[3][j] * bx, f12 = f[1][j] * ax + f[2][j] * bx;
+      const float f56 = f[5][j] * ax + f[6][j] * bx, f47 = f[4][j] * ax + f[7][j] * bx;
+      const float f0312 = f03 * ay + f12 * by, f4756 = f47 * ay + f56 * by;
+      gz += gr[j] * (f0312 - f4756);
+      gy += gr[j] * ((f03 - f12) * az + (f47 - f56) * bz);
+      gx += gr[j] * (((f[0][j] - f[3][j]) * ay + (f[1][j] - f[2][j]) * by) * az +
+                     ((f[4][j] - f[7][j]) * ay + (f[5][j] - f[6][j]) * by) * bz);
+    }
+    atomicAdd(dx + 3 * m + 0, gx * scal);
+    atomicAdd(dx + 3 * m + 1, gy * scal);
+    atomicAdd(dx + 3 * m + 2, gz * scal);
+  }
+  float w[8];
+  corner_weights(c, w);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) scatter_row<F>(dtable + level_off, c.row[k], gr, w[k]);
+}
+
+__global__ void __launch_bounds__(256) frustum_gaussians_kernel(const float* __restrict__ origins,
+                                                                const float* __restrict__ directions,
+                                                                const float* __restrict__ pixel_area,
+                                                                nrb_intervals_t iv, float scale,
+                                                                float* __restrict__ x, float* __restrict__ std,
+                                                                int64_t total) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int S = iv.num_samples;
+  const int64_t n = gid / S;
+  const int s = static_cast<int>(gid - n * S);
+  const Gaussian g = sample_gaussian(origins[3 * n], origins[3 * n + 1], origins[3 * n + 2], directions[3 * n],
+                                     directions[3 * n + 1], directions[3 * n + 2], pixel_area[n],
+                                     iv.starts[n * iv.row_stride + s], iv.ends[n * iv.row_stride + s], scale);
+  x[3 * gid + 0] = g.x;
+  x[3 * gid + 1] = g.y;
+  x[3 * gid + 2] = g.z;
+  std[gid] = g.std;
+}
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float* std, float* out, int64_t M,
+                            nrb_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  NRB_REQUIRE(x && out && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_fwd: null pointer or negative M");
+  NRB_REQUIRE(aligned16(out), NRB_ERR_ALIGNMENT, "nrb_hash_fwd: out must be 16-byte aligned");
+  if (M == 0) return NRB_OK;
+  const int64_t total = M * grid->num_levels;
+  const GridDev g = to_dev(grid);
+  auto s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = blocks_for(total, 256);
+  switch (grid->features_per_level) {
+    case 1: hash_fwd_kernel<1><<<blocks, 256, 0, s>>>(g, x, std, out, total); break;
+    case 2: hash_fwd_kernel<2><<<blocks, 256, 0, s>>>(g, x, std, out, total); break;
+    default: hash_fwd_kernel<4><<<blocks, 256, 0, s>>>(g, x, std, out, total); break;
+  }
+  return finish_launch("nrb_hash_fwd");
+}
+
+extern "C" int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t* idx, int64_t M,
+                                nrb_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  NRB_REQUIRE(x && idx && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_indices: null pointer or negative M");
+  if (M == 0) return NRB_OK;
+  const int64_t total = M * grid->num_levels;
+  hash_indices_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(to_dev(grid), x, idx,
+                                                                                             total);
+  return finish_launch("nrb_hash_indices");
+}
+
+extern "C" int nrb_hash_bwd(const nrb_grid_t* grid, const float* x, const float* std, const float* dy, float* dtable,
+                            float* dx, int64_t M, nrb_stream_t stream) {
+  if (int rc = check_grid(grid)) return rc;
+  NRB_REQUIRE(x && dy && dtable && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_bwd: null pointer or negative M");
+  NRB_REQUIRE(aligned16(dy) && aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_hash_bwd: dy/dtable must be 16-byte aligned");
+  if (M == 0) return NRB_OK;
+  const int64_t total = M * grid->num_levels;
+  const GridDev g = to_dev(grid);
+  auto s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = blocks_for(total, 256);
+  if (dx != nullptr) {
+    cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * M, s);
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: memset failed: %s", cudaGetErrorString(e));
+    switch (grid->features_per_level) {
+      case 1: hash_bwd_kernel<1, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+      case 2: hash_bwd_kernel<2, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+      default: hash_bwd_kernel<4, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+    }
+  } else {
+    switch (grid->features_per_level) {
+      case 1: hash_bwd_kernel<1, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+      case 2: hash_bwd_kernel<2, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+      default: hash_bwd_kernel<4, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
+    }
+  }
+  return finish_launch("nrb_hash_bwd");
+}
+
+extern "C" int nrb_frustum_gaussians(const nrb_rays_t* rays, const nrb_intervals_t* iv, float scale, float* x,
+                                     float* std, nrb_stream_t stream) {
+  if (int rc = check_rays(rays)) return rc;
+  if (int rc = check_intervals("nrb_frustum_gaussians", iv)) return rc;
+  NRB_REQUIRE(x && std, NRB_ERR_BAD_ARG, "nrb_frustum_gaussians: null output pointer");
+  NRB_REQUIRE(scale > 0.f, NRB_ERR_BAD_ARG, "nrb_frustum_gaussians: scale must be positive");
+  if (rays->num_rays == 0) return NRB_OK;
+  const int64_t total = rays->num_rays * iv->num_samples;
+  frustum_gaussians_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      rays->origins, rays->directions, rays->pixel_area, *iv, scale, x, std, total);
+  return finish_launch("nrb_frustum_gaussians");
+}

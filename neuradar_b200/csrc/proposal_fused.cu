@@ -1,0 +1,274 @@
+// Fused proposal round: sample gaussians -> contraction -> hash encode -> anti-alias level weights -> linear decoder
+// -> trunc_exp -> density-to-weights scan, one warp per ray, nothing but the per-sample results leaves the SM.
+// Semantics: NeuRADProposalField.get_density (nerfstudio/fields/neurad_field.py:208-213) followed by
+// RaySamples.get_weights (nerfstudio/cameras/rays.py:188-210); trunc_exp backward clamps the exponent to +-15
+// (nerfstudio/field_components/activations.py:28-41).
+#include "common.cuh"
+
+namespace nrb {
+
+constexpr int kPropWarps = 4;
+constexpr int kMaxChunks = NRB_MAX_SAMPLES / 32;
+
+struct PropGrid {
+  const float* table;
+  float scalings[NRB_MAX_LEVELS];
+  const float* decoder;  // [L*F] device pointer (density_decoder.weight)
+  int num_levels;
+  int log2_size;
+};
+
+template <int F, bool kSave>
+__global__ void __launch_bounds__(kPropWarps * 32) proposal_fwd_kernel(
+    const __grid_constant__ PropGrid g, const float* __restrict__ origins, const float* __restrict__ directions,
+    const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
+    float* __restrict__ density, float* __restrict__ weights, float* __restrict__ saved_feats,
+    float* __restrict__ saved_pre) {
+  __shared__ float s_dec[NRB_MAX_LEVELS * 4];
+  const int lane = threadIdx.x & 31;
+  const int S = iv.num_samples;
+  const int LF = g.num_levels * F;
+  if (threadIdx.x < NRB_MAX_LEVELS * 4) s_dec[threadIdx.x] = threadIdx.x < LF ? g.decoder[threadIdx.x] : 0.0f;
+  __syncthreads();
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * kPropWarps + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const float ox = origins[3 * n], oy = origins[3 * n + 1], oz = origins[3 * n + 2];
+  const float dx = directions[3 * n], dy = directions[3 * n + 1], dz = directions[3 * n + 2];
+  const float pa = pixel_area[n];
+  const float* st = iv.starts + n * iv.row_stride;
+  const float* en = iv.ends + n * iv.row_stride;
+  const uint32_t mask = (1u << g.log2_size) - 1u;
+  float carry = 0.0f;
+  for (int base = 0; base < S; base += 32) {
+    const int i = base + lane;
+    const bool ok = i < S;
+    float dd = 0.0f, dens = 0.0f;
+    if (ok) {
+      const float start = st[i], end = en[i];
+      const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, start, end, scale);
+      float pre = 0.0f;
+      for (int l = 0; l < g.num_levels; ++l) {
+        const float scal = g.scalings[l];
+        const Cell c = locate_cell(q.x, q.y, q.z, scal, mask);
+        float v[F];
+        interpolate<F>(g.table + (static_cast<size_t>(l) << g.log2_size) * F, c, v);
+        const float lw = level_weight(scal, q.std);
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+          const float f = v[j] * lw;
+          pre = fmaf(f, s_dec[l * F + j], pre);
+          if constexpr (kSave) saved_feats[(n * S + i) * LF + l * F + j] = f;
+        }
+      }
+      dens = expf(pre);
+      if constexpr (kSave) saved_pre[n * S + i] = pre;
+      if (density != nullptr) density[n * S + i] = dens;
+      dd = mul(sub(end, start), dens);
+    }
+    const float incl = warp_inclusive_sum(dd, lane);
+    float excl = __shfl_up_sync(kFull, incl, 1);
+    if (lane == 0) excl = 0.0f;
+    const float alpha = 1.0f - expf(-dd);
+    const float trans = expf(-(carry + excl));
+    if (ok) weights[n * S + i] = nan_to_num(alpha * trans);
+    carry += __shfl_sync(kFull, incl, 31);
+  }
+}
+
+template <int F>
+__global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
+    const __grid_constant__ PropGrid g, const float* __restrict__ origins, const float* __restrict__ directions,
+    const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
+    const float* __restrict__ saved_feats, const float* __restrict__ saved_pre, const float* __restrict__ dweights,
+    const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder) {
+  __shared__ float s_ddec[NRB_MAX_LEVELS * 4];
+  __shared__ float s_dec[NRB_MAX_LEVELS * 4];
+  const int lane = threadIdx.x & 31;
+  const int S = iv.num_samples;
+  const int LF = g.num_levels * F;
+  if (threadIdx.x < NRB_MAX_LEVELS * 4) {
+    s_ddec[threadIdx.x] = 0.0f;
+    s_dec[threadIdx.x] = threadIdx.x < LF ? g.decoder[threadIdx.x] : 0.0f;
+  }
+  __syncthreads();
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * kPropWarps + (threadIdx.x >> 5);
+  if (n < N) {
+    const float ox = origins[3 * n], oy = origins[3 * n + 1], oz = origins[3 * n + 2];
+    const float dx = directions[3 * n], dy = directions[3 * n + 1], dz = directions[3 * n + 2];
+    const float pa = pixel_area[n];
+    const float* st = iv.starts + n * iv.row_stride;
+    const float* en = iv.ends + n * iv.row_stride;
+    const uint32_t mask = (1u << g.log2_size) - 1u;
+    // forward recompute of the weight scan from the saved pre-activations
+    float delta[kMaxChunks], dd[kMaxChunks], trans[kMaxChunks], pre[kMaxChunks], gdens[kMaxChunks];
+    float carry = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (c * 32 < S) {
+        const int i = c * 32 + lane;
+        const bool ok = i < S;
+        pre[c] = ok ? saved_pre[n * S + i] : 0.0f;
+        delta[c] = ok ? sub(en[i], st[i]) : 0.0f;
+        dd[c] = ok ? mul(delta[c], expf(pre[c])) : 0.0f;
+        const float incl = warp_inclusive_sum(dd[c], lane);
+        float excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = 0.0f;
+        trans[c] = expf(-(carry + excl));
+        carry += __shfl_sync(kFull, incl, 31);
+      }
+    }
+    // d weights -> d density (reverse exclusive scan), see density_weights_bwd_kernel
+    float suffix = 0.0f;
+#pragma unroll
+    for (int c = kMaxChunks - 1; c >= 0; --c) {
+      if (c * 32 < S) {
+        const int i = c * 32 + lane;
+        const bool ok = i < S;
+        const float e = expf(-dd[c]);
+        const float w = (1.0f - e) * trans[c];
+        float gwt = (ok && dweights != nullptr) ? dweights[n * S + i] : 0.0f;
+        if (isnan(w) || isinf(w)) gwt = 0.0f;
+        const float gw = ok ? gwt * w : 0.0f;
+        float incl = gw;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float v = __shfl_down_sync(kFull, incl, o);
+          if (lane + o < 32) incl += v;
+        }
+        const float later = suffix + (incl - gw);
+        gdens[c] = ok ? (gwt * trans[c] * e - later) * delta[c] : 0.0f;
+        if (ok && ddensity != nullptr) gdens[c] += ddensity[n * S + i];
+        suffix += __shfl_sync(kFull, incl, 0);
+      }
+    }
+    // d density -> d pre (trunc_exp) -> decoder and table gradients
+    float ddec[NRB_MAX_LEVELS * F];
+#pragma unroll
+    for (int q = 0; q < NRB_MAX_LEVELS * F; ++q) ddec[q] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      if (c * 32 < S) {
+        const int i = c * 32 + lane;
+        if (i < S) {
+          const float gpre = gdens[c] * expf(fminf(fmaxf(pre[c], -15.0f), 15.0f));
+          const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, st[i], en[i], scale);
+          const float* sf = saved_feats + (n * S + i) * LF;
+#pragma unroll
+          for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
+            if (l < g.num_levels) {
+              const float scal = g.scalings[l];
+              const Cell cell = locate_cell(q.x, q.y, q.z, scal, mask);
+              const float lw = level_weight(scal, q.std);
+              float gr[F];
+#pragma unroll
+              for (int j = 0; j < F; ++j) {
+                ddec[l * F + j] = fmaf(gpre, sf[l * F + j], ddec[l * F + j]);
+                gr[j] = gpre * s_dec[l * F + j] * lw;
+              }
+              float w8[8];
+              corner_weights(cell, w8);
+              float* base = dtable + (static_cast<size_t>(l) << g.log2_size) * F;
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                float* p = base + static_cast<size_t>(cell.row[k]) * F;
+                if constexpr (F == 1) {
+                  atomicAdd(p, gr[0] * w8[k]);
+                } else if constexpr (F == 2) {
+                  atomicAdd(reinterpret_cast<float2*>(p), make_float2(gr[0] * w8[k], gr[1] * w8[k]));
+                } else {
+                  atomicAdd(reinterpret_cast<float4*>(p),
+                            make_float4(gr[0] * w8[k], gr[1] * w8[k], gr[2] * w8[k], gr[3] * w8[k]));
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NRB_MAX_LEVELS * F; ++q) {
+      if (q < LF) {
+        const float s = warp_sum(ddec[q]);
+        if (lane == 0) atomicAdd(&s_ddec[q], s);
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < LF && ddecoder != nullptr) atomicAdd(ddecoder + threadIdx.x, s_ddec[threadIdx.x]);
+}
+
+static PropGrid make_prop_grid(const nrb_grid_t* grid, const float* decoder) {
+  PropGrid out;
+  out.table = grid->table;
+  for (int i = 0; i < NRB_MAX_LEVELS; ++i) out.scalings[i] = grid->scalings[i];
+  out.decoder = decoder;
+  out.num_levels = grid->num_levels;
+  out.log2_size = grid->log2_hashmap_size;
+  return out;
+}
+
+static int check_proposal(const char* who, const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
+                          float scale, const nrb_intervals_t* iv) {
+  if (int rc = check_rays(rays)) return rc;
+  if (int rc = check_grid(grid)) return rc;
+  if (int rc = check_intervals(who, iv)) return rc;
+  NRB_REQUIRE(decoder_w != nullptr, NRB_ERR_BAD_ARG, "%s: null pointer", who);
+  NRB_REQUIRE(scale > 0.f, NRB_ERR_BAD_ARG, "%s: static_scale must be positive", who);
+  return NRB_OK;
+}
+
+}  // namespace nrb
+
+using namespace nrb;
+
+extern "C" int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
+                                float static_scale, const nrb_intervals_t* iv, float* density, float* weights,
+                                float* saved_feats, float* saved_pre, nrb_stream_t stream) {
+  if (int rc = check_proposal("nrb_proposal_fwd", rays, grid, decoder_w, static_scale, iv)) return rc;
+  NRB_REQUIRE(weights != nullptr, NRB_ERR_BAD_ARG, "nrb_proposal_fwd: weights is null");
+  NRB_REQUIRE((saved_feats == nullptr) == (saved_pre == nullptr), NRB_ERR_BAD_ARG,
+              "nrb_proposal_fwd: saved_feats and saved_pre must be given together");
+  const int64_t N = rays->num_rays;
+  if (N == 0) return NRB_OK;
+  const PropGrid g = make_prop_grid(grid, decoder_w);
+  const unsigned blocks = blocks_for(N, kPropWarps);
+  auto s = static_cast<cudaStream_t>(stream);
+  const bool save = saved_feats != nullptr;
+#define NRB_LAUNCH(F, SAVE)                                                                                          \
+  proposal_fwd_kernel<F, SAVE><<<blocks, kPropWarps * 32, 0, s>>>(g, rays->origins, rays->directions,               \
+                                                                  rays->pixel_area, static_scale, *iv, N,           \
+                                                                  density, weights, saved_feats, saved_pre)
+  switch (grid->features_per_level) {
+    case 1: if (save) NRB_LAUNCH(1, true); else NRB_LAUNCH(1, false); break;
+    case 2: if (save) NRB_LAUNCH(2, true); else NRB_LAUNCH(2, false); break;
+    default: if (save) NRB_LAUNCH(4, true); else NRB_LAUNCH(4, false); break;
+  }
+#undef NRB_LAUNCH
+  return finish_launch("nrb_proposal_fwd");
+}
+
+extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
+                                float static_scale, const nrb_intervals_t* iv, const float* saved_feats,
+                                const float* saved_pre, const float* dweights, const float* ddensity, float* dtable,
+                                float* ddecoder_w, nrb_stream_t stream) {
+  if (int rc = check_proposal("nrb_proposal_bwd", rays, grid, decoder_w, static_scale, iv)) return rc;
+  NRB_REQUIRE(saved_feats && saved_pre && dtable, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: null pointer");
+  NRB_REQUIRE(dweights || ddensity, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: no upstream gradient");
+  NRB_REQUIRE(aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_proposal_bwd: dtable must be 16-byte aligned");
+  const int64_t N = rays->num_rays;
+  if (N == 0) return NRB_OK;
+  const PropGrid g = make_prop_grid(grid, decoder_w);
+  const unsigned blocks = blocks_for(N, kPropWarps);
+  auto s = static_cast<cudaStream_t>(stream);
+#define NRB_LAUNCH(F)                                                                                              \
+  proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, rays->origins, rays->directions, rays->pixel_area,  \
+                                                            static_scale, *iv, N, saved_feats, saved_pre,          \
+                                                            dweights, ddensity, dtable, ddecoder_w)
+  switch (grid->features_per_level) {
+    case 1: NRB_LAUNCH(1); break;
+    case 2: NRB_LAUNCH(2); break;
+    default: NRB_LAUNCH(4); break;
+  }
+#undef NRB_LAUNCH
+  return finish_launch("nrb_proposal_bwd");
+}

@@ -1,0 +1,290 @@
+"""Field components of the hot path with the reference's constructor signatures and parameter names.
+
+HashEncoding   <- nerfstudio/field_components/encodings.py:311-471
+SHEncoding     <- nerfstudio/field_components/encodings.py:760-805
+MLP            <- nerfstudio/field_components/mlp.py:60-183
+NeuRADHashEncoding (+ StaticSettings / ActorSettings / NeuRADHashEncodingConfig)
+               <- nerfstudio/field_components/neurad_encoding.py:36-316
+trunc_exp, SigmoidDensity <- field_components/activations.py:28-52, model_components/utils.py:21-41
+
+State-dict keys match the reference's torch path (`hash_table`, `scalings`, `layers.{i}.weight|bias`, `beta`), so
+checkpoints are interchangeable with it.  `implementation` is accepted for signature compatibility; there is one
+implementation here: the CUDA kernels.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Set, Tuple, Type
+
+import numpy as np
+import torch
+from torch import Tensor, nn
+
+from . import functional as F
+from .rays import GaussiansStd
+
+
+def _warn_impl(implementation: str) -> None:
+    if implementation not in ("tcnn", "torch", "b200"):
+        raise ValueError(f"unknown implementation {implementation!r}")
+
+
+class HashEncoding(nn.Module):
+    """Multiresolution hash grid; forward = gather-bound CUDA kernel, backward = atomic scatter kernel."""
+
+    def __init__(
+        self,
+        num_levels: int = 16,
+        min_res: int = 16,
+        max_res: int = 1024,
+        log2_hashmap_size: int = 19,
+        features_per_level: int = 2,
+        hash_init_scale: float = 0.001,
+        implementation: str = "b200",
+        interpolation: Optional[str] = None,
+        n_input_dims: int = 3,
+    ) -> None:
+        super().__init__()
+        _warn_impl(implementation)
+        assert interpolation is None or interpolation == "Linear", f"interpolation '{interpolation}' is not supported"
+        if n_input_dims != 3:
+            raise NotImplementedError("only 3-D hash grids are on the NeuRadar torch path")
+        if features_per_level not in (1, 2, 4):
+            raise NotImplementedError("features_per_level must be 1, 2 or 4")
+        self.in_dim = 3
+        self.num_levels = num_levels
+        self.min_res = min_res
+        self.max_res = max_res
+        self.features_per_level = features_per_level
+        self.hash_init_scale = hash_init_scale
+        self.log2_hashmap_size = log2_hashmap_size
+        self.hash_table_size = 2**log2_hashmap_size
+
+        # identical expressions to encodings.py:348-352 so that the fp32 level resolutions agree bit for bit
+        levels = torch.arange(num_levels)
+        self.growth_factor = np.exp((np.log(max_res) - np.log(min_res)) / (num_levels - 1)) if num_levels > 1 else 1.0
+        self.register_buffer("scalings", torch.floor(min_res * self.growth_factor**levels))
+        self.hash_offset = levels * self.hash_table_size
+        self.tcnn_encoding = None
+
+        table = torch.rand(size=(self.hash_table_size * num_levels, features_per_level)) * 2 - 1
+        self.hash_table = nn.Parameter(table * hash_init_scale)
+        self._spec = F.GridSpec(num_levels, features_per_level, log2_hashmap_size, tuple(float(s) for s in self.scalings))
+
+    @property
+    def spec(self) -> F.GridSpec:
+        return self._spec
+
+    def get_out_dim(self) -> int:
+        return self.num_levels * self.features_per_level
+
+    def hash_fn(self, in_tensor: Tensor) -> Tensor:
+        """Rows of integer grid coordinates [..., L, 3] -> [..., L] int64 (encodings.py:406-423), for inspection."""
+        c = in_tensor.to(torch.int64)
+        h = c[..., 0] ^ (c[..., 1] * 2654435761) ^ (c[..., 2] * 805459861)
+        return torch.remainder(h, self.hash_table_size) + self.hash_offset.to(h.device)
+
+    def corner_indices(self, in_tensor: Tensor) -> Tensor:
+        """Rows gathered for each point: [*bs, L, 8] int64, computed by the CUDA kernel."""
+        flat = in_tensor.reshape(-1, 3)
+        return F.hash_indices(flat, self._spec).view(*in_tensor.shape[:-1], self.num_levels, 8)
+
+    def forward(self, in_tensor: Tensor, std: Optional[Tensor] = None) -> Tensor:
+        assert in_tensor.shape[-1] == 3
+        flat = in_tensor.reshape(-1, 3)
+        out = F.hash_encode(flat, self.hash_table, self._spec, None if std is None else std.reshape(-1))
+        return out.view(*in_tensor.shape[:-1], self.get_out_dim())
+
+
+class SHEncoding(nn.Module):
+    """Degree-4 spherical harmonics (16 components); no gradient, like the reference's torch path."""
+
+    def __init__(self, levels: int = 4, implementation: str = "b200") -> None:
+        super().__init__()
+        _warn_impl(implementation)
+        if levels != 4:
+            raise NotImplementedError("the B200 kernel implements the 4-level encoding NeuRadar uses")
+        self.in_dim = 3
+        self.levels = levels
+
+    def get_out_dim(self) -> int:
+        return self.levels**2
+
+    @torch.no_grad()
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        out = F.sh16(in_tensor.reshape(-1, 3), normalize_to_unit_cube=False)
+        return out.view(*in_tensor.shape[:-1], 16)
+
+
+class MLP(nn.Module):
+    """Linear+ReLU chain evaluated by the fused MLP kernels (ReLU hidden activation, no output activation)."""
+
+    def __init__(
+        self,
+        in_dim: int,
+        num_layers: int,
+        layer_width: int,
+        out_dim: Optional[int] = None,
+        skip_connections: Optional[Tuple[int]] = None,
+        activation: Optional[nn.Module] = nn.ReLU(),
+        out_activation: Optional[nn.Module] = None,
+        implementation: str = "b200",
+    ) -> None:
+        super().__init__()
+        _warn_impl(implementation)
+        assert in_dim > 0
+        if skip_connections:
+            raise NotImplementedError("skip connections are not used on the NeuRadar path")
+        if not isinstance(activation, nn.ReLU):
+            raise NotImplementedError("hidden activation must be ReLU")
+        self.in_dim = in_dim
+        self.out_dim = out_dim if out_dim is not None else layer_width
+        self.num_layers = num_layers
+        self.layer_width = layer_width
+        self.skip_connections = skip_connections
+        self._skip_connections: Set[int] = set()
+        self.activation = activation
+        self.out_activation = out_activation
+        self.tcnn_encoding = None
+        dims = [in_dim] + [layer_width] * (num_layers - 1) + [self.out_dim]
+        self.layers = nn.ModuleList([nn.Linear(dims[i], dims[i + 1]) for i in range(num_layers)])
+
+    def get_out_dim(self) -> int:
+        return self.out_dim
+
+    def forward(self, in_tensor: Tensor) -> Tensor:
+        flat = in_tensor.reshape(-1, self.in_dim)
+        y = F.mlp_forward(flat, [l.weight for l in self.layers], [l.bias for l in self.layers])
+        y = y.view(*in_tensor.shape[:-1], self.out_dim)
+        if self.out_activation is not None:
+            y = self.out_activation(y)
+        return y
+
+
+class _TruncExp(torch.autograd.Function):
+    """exp with the backward exponent clamped to [-15, 15] (activations.py:28-41)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return torch.exp(x)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        return g * torch.exp(ctx.saved_tensors[0].clamp(-15, 15))
+
+
+trunc_exp = _TruncExp.apply
+
+
+class SigmoidDensity(nn.Module):
+    """alpha = sigmoid(-sdf * (|beta| + beta_min)) (model_components/utils.py:21-41)."""
+
+    def __init__(self, init_val, beta_min=0.0001, learnable_beta=False):
+        super().__init__()
+        self.register_buffer("beta_min", torch.tensor(beta_min))
+        self.register_parameter("beta", nn.Parameter(init_val * torch.ones(1), requires_grad=learnable_beta))
+
+    def forward(self, sdf: Tensor, beta: Optional[Tensor] = None) -> Tensor:
+        if beta is None:
+            beta = self.get_beta()
+        return torch.sigmoid(-sdf * beta)
+
+    def get_beta(self):
+        return self.beta.abs() + self.beta_min
+
+
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class StaticSettings:
+    hashgrid_dim: int = 4
+    num_levels: int = 8
+    base_res: int = 32
+    max_res: int = 8192
+    log2_hashmap_size: int = 22
+
+
+@dataclass
+class ActorSettings:
+    flip_prob: float = 0.5
+    actor_scale: float = 10.0
+    hashgrid_dim: int = 4
+    num_levels: int = 4
+    base_res: int = 64
+    max_res: int = 1024
+    log2_hashmap_size: int = 17
+    use_4d_hashgrid: bool = True
+
+
+@dataclass
+class NeuRADHashEncodingConfig:
+    _target: Type = field(default_factory=lambda: NeuRADHashEncoding)
+    static: StaticSettings = field(default_factory=StaticSettings)
+    actor: ActorSettings = field(default_factory=ActorSettings)
+    disable_actors: bool = False
+    require_actor_grad: bool = True
+
+    def setup(self, **kwargs):
+        return self._target(self, **kwargs)
+
+
+class NoActors:
+    """Stand-in for DynamicActors with zero trajectories (model_components/dynamic_actors.py): static scenes."""
+
+    n_actors = 0
+
+
+class NeuRADHashEncoding(nn.Module):
+    """Static-world hash grid with contraction and per-level anti-alias weights
+    (neurad_encoding.py:87-189,277-280,309-316).  Dynamic actors are row "next-3" of SURVEY.md 8f and are not
+    part of this round: constructing with n_actors > 0 raises."""
+
+    def __init__(self, config: NeuRADHashEncodingConfig, dynamic_actors=None, static_scale: float = 1.0,
+                 implementation: str = "b200") -> None:
+        super().__init__()
+        _warn_impl(implementation)
+        self.config = config
+        self.implementation = implementation
+        self.actors = dynamic_actors if dynamic_actors is not None else NoActors()
+        if getattr(self.actors, "n_actors", 0) > 0 and not config.disable_actors:
+            raise NotImplementedError("dynamic-actor grids are not implemented yet (SURVEY.md 8f, next-3)")
+        self.static_scale = float(static_scale)
+        self.static_grid = HashEncoding(
+            features_per_level=config.static.hashgrid_dim,
+            num_levels=config.static.num_levels,
+            min_res=config.static.base_res,
+            max_res=config.static.max_res,
+            log2_hashmap_size=config.static.log2_hashmap_size,
+        )
+        self.actor_grids = nn.ModuleList([])
+        self.scene_repr_dim = self.static_grid.get_out_dim()
+
+    def get_out_dim(self) -> int:
+        return self.scene_repr_dim
+
+    def get_param_groups(self, param_groups: Dict):
+        param_groups["hashgrids"] += list(self.static_grid.parameters()) + list(self.actor_grids.parameters())
+
+    def forward(self, positions: GaussiansStd, times: Optional[Tensor] = None, directions: Optional[Tensor] = None):
+        """World-space gaussians (mean [N,S,1,3], std [N,S,1,1]) -> (features [N*S, L*F], directions)."""
+        mean = positions.mean.reshape(-1, 3)
+        std = positions.std.reshape(-1, 1)
+        # ScaledSceneContraction(order=inf, scale=static_scale), spatial_distortions.py:103-113,132-136
+        mean = mean / self.static_scale
+        std = std / self.static_scale
+        mag = mean.abs().amax(dim=-1, keepdim=True)
+        cm = mag.clamp_min(1.0)
+        inside = mag < 1
+        mean = torch.where(inside, mean, (2 - (1 / cm)) * (mean / cm))
+        std = torch.where(inside, std, std * ((2 * cm - 1).pow(1 / 3) / cm) ** 2)
+        mean = (mean + 2.0) / 4.0
+        std = std / 4.0
+        feats = self.static_grid(mean, std=std)
+        return feats, directions
+
+    def encode_samples(self, rays: F.RayData, iv: F.SampleIntervals) -> Tensor:
+        """Fast path from per-ray data: gaussians + contraction in one kernel, then the weighted hash encode."""
+        x, std = F.frustum_gaussians(rays, iv, self.static_scale)
+        return F.hash_encode(x, self.static_grid.hash_table, self.static_grid.spec, std)

@@ -1,0 +1,168 @@
+"""NeuRAD fields with the reference's API: `forward(ray_samples)`, `get_density(ray_samples)`, `get_outputs`.
+
+NeuRADField / NeuRADFieldConfig                   <- nerfstudio/fields/neurad_field.py:45-152
+NeuRADProposalField / NeuRADProposalFieldConfig   <- nerfstudio/fields/neurad_field.py:155-216
+Field base API (`get_density`, `get_outputs`, `forward`) <- nerfstudio/fields/base_field.py:40-133
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from enum import Enum
+from typing import Dict, Optional, Tuple, Type
+
+import torch
+from torch import Tensor, nn
+
+from . import functional as F
+from .field_components import (
+    MLP,
+    ActorSettings,
+    NeuRADHashEncoding,
+    NeuRADHashEncodingConfig,
+    SHEncoding,
+    SigmoidDensity,
+    StaticSettings,
+    trunc_exp,
+)
+from .rays import RaySamples
+
+
+class FieldHeadNames(Enum):
+    """Subset of nerfstudio/field_components/field_heads.py used on the path."""
+
+    FEATURE = "feature"
+    DENSITY = "density"
+    SDF = "sdf"
+    ALPHA = "alpha"
+
+
+def get_normalized_directions(directions: Tensor) -> Tensor:
+    """(d + 1) / 2 (fields/base_field.py:136-142)."""
+    return (directions + 1.0) / 2.0
+
+
+@dataclass
+class NeuRADFieldConfig:
+    _target: Type = field(default_factory=lambda: NeuRADField)
+    grid: NeuRADHashEncodingConfig = field(
+        default_factory=lambda: NeuRADHashEncodingConfig(require_actor_grad=True, actor=ActorSettings(flip_prob=0.25))
+    )
+    geo_hidden_dim: int = 32
+    geo_num_layers: int = 2
+    nff_hidden_dim: int = 32
+    nff_num_layers: int = 3
+    nff_out_dim: int = 32
+    num_multisamples: int = 1
+    use_sdf: bool = True
+    sdf_beta: float = 20.0
+    learnable_beta: bool = True
+
+    def setup(self, **kwargs):
+        return self._target(self, **kwargs)
+
+
+class NeuRADField(nn.Module):
+    """hash grid -> geometry MLP -> (sdf | embedding) -> SH(direction) -> feature MLP + residual; alpha from the sdf."""
+
+    def __init__(self, config: NeuRADFieldConfig, actors=None, static_scale: float = 1.0, implementation: str = "b200"):
+        super().__init__()
+        self.config = config
+        self.implementation = implementation
+        if config.num_multisamples != 1:
+            raise NotImplementedError("num_multisamples must be 1")
+        self.hashgrid: NeuRADHashEncoding = config.grid.setup(dynamic_actors=actors, static_scale=static_scale)
+        self.geo_feat_dim = config.nff_out_dim
+        self.mlp_geo = MLP(
+            in_dim=self.hashgrid.get_out_dim(),
+            num_layers=config.geo_num_layers,
+            layer_width=config.geo_hidden_dim,
+            out_dim=self.geo_feat_dim + 1,
+        )
+        self.direction_encoding = SHEncoding(levels=4)
+        self.mlp_feature = MLP(
+            in_dim=self.direction_encoding.get_out_dim() + self.geo_feat_dim,
+            num_layers=config.nff_num_layers,
+            layer_width=config.nff_hidden_dim,
+            out_dim=config.nff_out_dim,
+        )
+        if config.use_sdf:
+            self.sdf_to_density = SigmoidDensity(config.sdf_beta, learnable_beta=config.learnable_beta)
+
+    def get_param_groups(self, param_groups: Dict):
+        self.hashgrid.get_param_groups(param_groups)
+        param_groups["fields"] += list(self.mlp_geo.parameters()) + list(self.mlp_feature.parameters())
+        if self.config.use_sdf:
+            param_groups["fields"] += list(self.sdf_to_density.parameters())
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
+        if compute_normals:
+            raise NotImplementedError("normals are not rendered on the NeuRadar path")
+        rays, iv = ray_samples.per_ray()
+        N, S = rays.num_rays, iv.num_samples
+        features = self.hashgrid.encode_samples(rays, iv)
+        geo = self.mlp_geo(features)
+        geo_out, geo_embedding = torch.split(geo, [1, self.geo_feat_dim], dim=-1)
+        # directions are per ray: evaluate the 16 SH values once per ray and broadcast over the samples
+        sh = self.direction_encoding(get_normalized_directions(rays.directions))
+        sh = sh[:, None, :].expand(N, S, 16).reshape(N * S, 16)
+        feature = geo_embedding + self.mlp_feature(torch.cat([geo_embedding, sh], dim=-1))
+        shape = ray_samples.shape if len(ray_samples.shape) == 2 else (N, S)
+        outputs = {FieldHeadNames.FEATURE: feature.view(*shape, self.config.nff_out_dim)}
+        geo_out = geo_out.reshape(*shape, 1)
+        if self.config.use_sdf:
+            outputs[FieldHeadNames.SDF] = geo_out
+            outputs[FieldHeadNames.ALPHA] = self.sdf_to_density(geo_out)
+        else:
+            outputs[FieldHeadNames.DENSITY] = trunc_exp(geo_out)
+        return outputs
+
+
+@dataclass
+class NeuRADProposalFieldConfig:
+    _target: Type = field(default_factory=lambda: NeuRADProposalField)
+    grid: NeuRADHashEncodingConfig = field(
+        default_factory=lambda: NeuRADHashEncodingConfig(
+            static=StaticSettings(log2_hashmap_size=20, num_levels=6, max_res=4096, base_res=128, hashgrid_dim=1),
+            actor=ActorSettings(log2_hashmap_size=15, num_levels=4, base_res=64, max_res=1024, hashgrid_dim=1),
+            require_actor_grad=False,
+        )
+    )
+    hidden_dim: int = 16
+
+    def setup(self, **kwargs):
+        return self._target(self, **kwargs)
+
+
+class NeuRADProposalField(nn.Module):
+    """hash grid -> Linear(L*F, 1, bias=False) -> trunc_exp.  `get_density` runs the fused proposal kernel."""
+
+    def __init__(self, config: NeuRADProposalFieldConfig, actors=None, static_scale: float = 1.0,
+                 implementation: str = "b200"):
+        super().__init__()
+        self.config = config
+        self.implementation = implementation
+        self.hashgrid: NeuRADHashEncoding = config.grid.setup(dynamic_actors=actors, static_scale=static_scale)
+        self.density_decoder = nn.Linear(self.hashgrid.get_out_dim(), 1, bias=False)
+
+    def get_param_groups(self, param_groups: Dict):
+        self.hashgrid.get_param_groups(param_groups)
+        param_groups["fields"] += list(self.density_decoder.parameters())
+
+    def density_and_weights(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
+        """One kernel for get_density + RaySamples.get_weights: ([N,S,1], [N,S,1])."""
+        rays, iv = ray_samples.per_ray()
+        grid = self.hashgrid.static_grid
+        dens, w = F.proposal_round(grid.hash_table, self.density_decoder.weight, rays, iv, grid.spec,
+                                   self.hashgrid.static_scale)
+        return dens.unsqueeze(-1), w.unsqueeze(-1)
+
+    def get_density(self, ray_samples: RaySamples) -> Tuple[Tensor, None]:
+        dens, _ = self.density_and_weights(ray_samples)
+        return dens.view(*ray_samples.shape, 1), None
+
+    def get_outputs(self, ray_samples: RaySamples, density_embedding: Optional[Tensor] = None) -> dict:
+        return {}
+
+    def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
+        density, _ = self.get_density(ray_samples)
+        return {FieldHeadNames.DENSITY: density}

@@ -1,0 +1,504 @@
+"""Autograd-aware wrappers around the C ABI.  Every function here launches hand-written sm_100a kernels from
+libneuradar_b200.so on the current CUDA stream; none has a PyTorch or CPU implementation.
+
+Shapes follow the reference: N rays, S samples per ray, M = N*S points, L levels, F features per level.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch import Tensor
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib
+from ._lib import Grid, Intervals, Mlp, MlpGrad, Rays, Spacing, check, f32c, ptr, stream_ptr
+
+
+# ------------------------------------------------------------------------------------------------
+# plain-data descriptors
+# ------------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class GridSpec:
+    """Static description of one HashEncoding (reference: field_components/encodings.py:326-352)."""
+
+    num_levels: int
+    features_per_level: int
+    log2_hashmap_size: int
+    scalings: Tuple[float, ...]
+
+    @property
+    def out_dim(self) -> int:
+        return self.num_levels * self.features_per_level
+
+    @property
+    def rows(self) -> int:
+        return self.num_levels << self.log2_hashmap_size
+
+    @property
+    def tag(self) -> str:
+        return f"L{self.num_levels}F{self.features_per_level}T{self.log2_hashmap_size}"
+
+    def struct(self, table: Tensor) -> Grid:
+        if table.shape != (self.rows, self.features_per_level):
+            raise ValueError(f"hash_table has shape {tuple(table.shape)}, expected {(self.rows, self.features_per_level)}")
+        g = Grid()
+        g.table = ptr(table)
+        for i, s in enumerate(self.scalings):
+            g.scalings[i] = s
+        g.num_levels = self.num_levels
+        g.features_per_level = self.features_per_level
+        g.log2_hashmap_size = self.log2_hashmap_size
+        return g
+
+
+@dataclass
+class RayData:
+    """Per-ray tensors of a RayBundle, un-broadcast and contiguous: origins/directions [N,3], the rest [N]."""
+
+    origins: Tensor
+    directions: Tensor
+    pixel_area: Tensor
+    nears: Optional[Tensor] = None
+    fars: Optional[Tensor] = None
+
+    def __post_init__(self):
+        self.origins = f32c(self.origins)
+        self.directions = f32c(self.directions)
+        self.pixel_area = f32c(self.pixel_area.reshape(-1))
+        if self.nears is not None:
+            self.nears = f32c(self.nears.reshape(-1))
+        if self.fars is not None:
+            self.fars = f32c(self.fars.reshape(-1))
+
+    @property
+    def num_rays(self) -> int:
+        return self.origins.shape[0]
+
+    def struct(self) -> Rays:
+        r = Rays()
+        r.origins, r.directions, r.pixel_area = ptr(self.origins), ptr(self.directions), ptr(self.pixel_area)
+        r.nears, r.fars = ptr(self.nears), ptr(self.fars)
+        r.num_rays = self.num_rays
+        return r
+
+
+class SampleIntervals:
+    """starts/ends [N,S] of the samples along each ray.  Views of one [N,S+1] bin tensor are passed through
+    without a copy (row stride S+1), which is how every sampler on the path produces them."""
+
+    def __init__(self, starts: Tensor, ends: Tensor):
+        if starts.dim() == 3:
+            starts, ends = starts[..., 0], ends[..., 0]
+        if starts.shape != ends.shape or starts.dim() != 2:
+            raise ValueError("starts/ends must both be [N,S] (or [N,S,1])")
+        ok = (
+            starts.dtype == torch.float32
+            and ends.dtype == torch.float32
+            and starts.stride(1) == 1
+            and ends.stride(1) == 1
+            and starts.stride(0) == ends.stride(0)
+            and starts.stride(0) >= starts.shape[1]
+        )
+        if not ok:
+            starts, ends = f32c(starts), f32c(ends)
+        self.starts, self.ends = starts, ends
+
+    @classmethod
+    def from_bins(cls, bins: Tensor) -> "SampleIntervals":
+        bins = f32c(bins)
+        return cls(bins[:, :-1], bins[:, 1:])
+
+    @property
+    def num_samples(self) -> int:
+        return self.starts.shape[1]
+
+    def struct(self) -> Intervals:
+        if not self.starts.is_cuda:
+            raise _lib.NeuradarB200Error("neuradar_b200 ops need CUDA tensors; there is no CPU path")
+        iv = Intervals()
+        iv.starts, iv.ends = self.starts.data_ptr(), self.ends.data_ptr()
+        iv.row_stride = self.starts.stride(0) if self.starts.shape[0] > 1 else max(self.starts.stride(0), self.num_samples)
+        iv.num_samples = self.num_samples
+        return iv
+
+
+def _lib_():
+    return _lib.load()
+
+
+# ------------------------------------------------------------------------------------------------
+# hash grid
+# ------------------------------------------------------------------------------------------------
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, table, std, spec: GridSpec):
+        x = f32c(x)
+        table = f32c(table)
+        std = None if std is None else f32c(std.reshape(-1))
+        M = x.shape[0]
+        out = torch.empty((M, spec.out_dim), device=x.device, dtype=torch.float32)
+        g = spec.struct(table)
+        _lib.call("nrb_hash_fwd", C.byref(g), ptr(x), ptr(std), ptr(out), M, stream_ptr(), tag="nrb_hash_fwd:" + spec.tag)
+        ctx.save_for_backward(x, table, std)
+        ctx.spec = spec
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        x, table, std = ctx.saved_tensors
+        spec = ctx.spec
+        dy = f32c(dy)
+        need_dx = ctx.needs_input_grad[0]
+        dtable = torch.zeros_like(table)
+        dx = torch.empty_like(x) if need_dx else None
+        g = spec.struct(table)
+        _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], stream_ptr(),
+                  tag="nrb_hash_bwd:" + spec.tag)
+        return dx, dtable, None, None
+
+
+def hash_encode(x: Tensor, table: Tensor, spec: GridSpec, std: Optional[Tensor] = None) -> Tensor:
+    """HashEncoding.forward on points x [M,3]; with `std` [M] also applies the per-level anti-alias weights."""
+    return _HashEncode.apply(x, table, std, spec)
+
+
+def hash_indices(x: Tensor, spec: GridSpec) -> Tensor:
+    """Table rows of the 8 cell corners, [M, L, 8] int64 (corner order of encodings.py:436-443)."""
+    x = f32c(x)
+    M = x.shape[0]
+    idx = torch.empty((M, spec.num_levels, 8), device=x.device, dtype=torch.int64)
+    g = Grid()
+    g.table = ptr(x)  # unused by the kernel, must be non-null and aligned
+    for i, s in enumerate(spec.scalings):
+        g.scalings[i] = s
+    g.num_levels, g.features_per_level, g.log2_hashmap_size = spec.num_levels, spec.features_per_level, spec.log2_hashmap_size
+    _lib.call("nrb_hash_indices", C.byref(g), ptr(x), ptr(idx), M, stream_ptr())
+    return idx
+
+
+def frustum_gaussians(rays: RayData, iv: SampleIntervals, scale: float) -> Tuple[Tensor, Tensor]:
+    """Contracted sample means [N*S,3] and stds [N*S] (get_fast_isotropic_gaussian(1) + ScaledSceneContraction)."""
+    N, S = rays.num_rays, iv.num_samples
+    x = torch.empty((N * S, 3), device=rays.origins.device, dtype=torch.float32)
+    std = torch.empty((N * S,), device=rays.origins.device, dtype=torch.float32)
+    r, i = rays.struct(), iv.struct()
+    _lib.call("nrb_frustum_gaussians", C.byref(r), C.byref(i), float(scale), ptr(x), ptr(std), stream_ptr())
+    return x, std
+
+
+# ------------------------------------------------------------------------------------------------
+# tiny MLP
+# ------------------------------------------------------------------------------------------------
+def _mlp_struct(dims: Sequence[int], weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]]) -> Mlp:
+    m = Mlp()
+    m.num_layers = len(weights)
+    for i, d in enumerate(dims):
+        m.dims[i] = d
+    for i, (w, b) in enumerate(zip(weights, biases)):
+        m.weights[i] = ptr(w)
+        m.biases[i] = ptr(b)
+    return m
+
+
+class _MlpForward(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, n_layers: int, *params):
+        weights = [f32c(w) for w in params[:n_layers]]
+        biases = [None if b is None else f32c(b) for b in params[n_layers:]]
+        x = f32c(x)
+        dims = [weights[0].shape[1]] + [w.shape[0] for w in weights]
+        if x.shape[-1] != dims[0]:
+            raise ValueError(f"MLP input has {x.shape[-1]} features, expected {dims[0]}")
+        M = x.shape[0]
+        y = torch.empty((M, dims[-1]), device=x.device, dtype=torch.float32)
+        n_hidden = sum(dims[1:-1])
+        keep = any(ctx.needs_input_grad) and n_hidden > 0
+        hidden = torch.empty((n_hidden, M), device=x.device, dtype=torch.float32) if keep else None
+        m = _mlp_struct(dims, weights, biases)
+        _lib.call("nrb_mlp_fwd", C.byref(m), ptr(x), ptr(y), ptr(hidden), M, stream_ptr(), tag="nrb_mlp_fwd:" + "x".join(map(str, dims)))
+        ctx.save_for_backward(x, hidden, *weights, *[b for b in biases if b is not None])
+        ctx.has_bias = [b is not None for b in biases]
+        ctx.dims = dims
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dy):
+        saved = ctx.saved_tensors
+        x, hidden = saved[0], saved[1]
+        n = len(ctx.dims) - 1
+        weights = list(saved[2 : 2 + n])
+        rest = list(saved[2 + n :])
+        biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+        dy = f32c(dy)
+        M = x.shape[0]
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dws = [torch.zeros_like(w) for w in weights]
+        dbs = [None if b is None else torch.zeros_like(b) for b in biases]
+        m = _mlp_struct(ctx.dims, weights, biases)
+        g = MlpGrad()
+        for i in range(n):
+            g.weights[i] = ptr(dws[i])
+            g.biases[i] = ptr(dbs[i])
+        _lib.call("nrb_mlp_bwd", C.byref(m), ptr(x), ptr(hidden), ptr(dy), ptr(dx), C.byref(g), M, stream_ptr(),
+                  tag="nrb_mlp_bwd:" + "x".join(map(str, ctx.dims)))
+        return (dx, None, *dws, *dbs)
+
+
+def mlp_forward(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]]) -> Tensor:
+    """Linear+ReLU chain on x [M, in] (no output activation), MLP.pytorch_fwd semantics."""
+    return _MlpForward.apply(x, len(weights), *weights, *biases)
+
+
+def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:
+    """16 real SH basis values of directions [M,3]; no gradient (reference: torch.no_grad)."""
+    d = f32c(directions.detach())
+    out = torch.empty((d.shape[0], 16), device=d.device, dtype=torch.float32)
+    _lib.call("nrb_sh16", ptr(d), ptr(out), d.shape[0], int(normalize_to_unit_cube), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# samplers (no gradients: bins are detached in the reference, ray_samplers.py:364)
+# ------------------------------------------------------------------------------------------------
+_LINSPACE_CACHE = {}
+
+
+def _linspace(start: float, end: float, steps: int, device) -> Tensor:
+    """torch.linspace evaluated on the CPU exactly like the reference does, cached per device."""
+    key = (start, end, steps, str(device))
+    t = _LINSPACE_CACHE.get(key)
+    if t is None:
+        t = torch.linspace(start, end, steps).to(device)
+        _LINSPACE_CACHE[key] = t
+    return t
+
+
+def spaced_bins(rays: RayData, num_samples: int, jitter: Optional[Tensor], lam: float, scaling: float) -> Tuple[Tensor, Tensor]:
+    """PowerSampler bins: spacing bins and euclidean bins, both [N, S+1].  jitter: [N,1]/[N] or [N,S+1] or None."""
+    N = rays.num_rays
+    dev = rays.origins.device
+    base = _linspace(0.0, 1.0, num_samples + 1, dev)
+    sbins = torch.empty((N, num_samples + 1), device=dev, dtype=torch.float32)
+    ebins = torch.empty_like(sbins)
+    per_bin = 0
+    if jitter is not None:
+        jitter = f32c(jitter)
+        if jitter.numel() == N * (num_samples + 1) and num_samples > 0 and jitter.dim() == 2 and jitter.shape[1] == num_samples + 1:
+            per_bin = 1
+        elif jitter.numel() != N:
+            raise ValueError("jitter must be [N,1] or [N,S+1]")
+    r = rays.struct()
+    _lib.call("nrb_spaced_bins", C.byref(r), Spacing(lam, scaling), ptr(base), ptr(jitter), per_bin, num_samples,
+                                ptr(sbins), ptr(ebins), stream_ptr())
+    return sbins, ebins
+
+
+def pdf_sample(
+    rays: RayData,
+    weights: Tensor,
+    sbins_in: Tensor,
+    num_samples: int,
+    jitter: Optional[Tensor],
+    lam: float,
+    scaling: float,
+    histogram_padding: float = 0.01,
+    eps: float = 1e-5,
+    return_debug: bool = False,
+):
+    """PDFSampler (include_original=False): new spacing/euclidean bins [N, S_out+1] from weights [N,S_in]."""
+    weights = f32c(weights.detach())
+    sbins_in = f32c(sbins_in)
+    N, S_in = weights.shape
+    if sbins_in.shape != (N, S_in + 1):
+        raise ValueError(f"existing bins have shape {tuple(sbins_in.shape)}, expected {(N, S_in + 1)}")
+    dev = weights.device
+    nb = num_samples + 1
+    u_base = _linspace(0.0, 1.0 - (1.0 / nb), nb, dev)
+    if jitter is not None:
+        jitter = f32c(jitter.reshape(-1))
+        if jitter.numel() != N:
+            raise ValueError("jitter must hold one value per ray (single_jitter)")
+    sb = torch.empty((N, nb), device=dev, dtype=torch.float32)
+    eb = torch.empty_like(sb)
+    inds = torch.empty((N, nb), device=dev, dtype=torch.int64) if return_debug else None
+    cdf = torch.empty((N, S_in + 1), device=dev, dtype=torch.float32) if return_debug else None
+    r = rays.struct()
+    _lib.call("nrb_pdf_sample", C.byref(r), Spacing(lam, scaling), ptr(weights), ptr(sbins_in), S_in, ptr(u_base),
+                               ptr(jitter), num_samples, float(histogram_padding), float(eps), ptr(sb), ptr(eb),
+                               ptr(inds), ptr(cdf), stream_ptr())
+    if return_debug:
+        return sb, eb, inds, cdf
+    return sb, eb
+
+
+# ------------------------------------------------------------------------------------------------
+# compositing
+# ------------------------------------------------------------------------------------------------
+class _DensityWeights(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, densities, iv: SampleIntervals):
+        dens = f32c(densities)
+        N, S = dens.shape
+        w = torch.empty_like(dens)
+        i = iv.struct()
+        _lib.call("nrb_density_weights_fwd", ptr(dens), C.byref(i), N, ptr(w), stream_ptr())
+        ctx.save_for_backward(dens)
+        ctx.iv = iv
+        return w
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dw):
+        (dens,) = ctx.saved_tensors
+        dw = f32c(dw)
+        dd = torch.empty_like(dens)
+        i = ctx.iv.struct()
+        _lib.call("nrb_density_weights_bwd", ptr(dens), C.byref(i), ptr(dw), dens.shape[0], ptr(dd), stream_ptr())
+        return dd, None
+
+
+def density_weights(densities: Tensor, iv: SampleIntervals) -> Tensor:
+    """RaySamples.get_weights: densities [N,S] -> weights [N,S]."""
+    return _DensityWeights.apply(densities, iv)
+
+
+class _AlphaComposite(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, alphas, feats, iv: SampleIntervals, trans_eps: float, sky: bool):
+        alphas = f32c(alphas)
+        N, S = alphas.shape
+        dev = alphas.device
+        feats = None if feats is None else f32c(feats)
+        Cn = 0 if feats is None else feats.shape[-1]
+        weights = torch.empty_like(alphas)
+        trans = torch.empty_like(alphas)
+        features = torch.empty((N, Cn), device=dev, dtype=torch.float32) if feats is not None else None
+        depth = torch.empty((N,), device=dev, dtype=torch.float32)
+        acc = torch.empty((N,), device=dev, dtype=torch.float32)
+        i = iv.struct()
+        _lib.call("nrb_alpha_composite_fwd", ptr(alphas), ptr(feats), C.byref(i), N, Cn, float(trans_eps), int(sky),
+                                            ptr(weights), ptr(features), ptr(depth), ptr(acc), ptr(trans),
+                                            stream_ptr())
+        ctx.save_for_backward(alphas, feats)
+        ctx.iv, ctx.eps, ctx.sky, ctx.C = iv, float(trans_eps), int(sky), Cn
+        if features is None:
+            features = torch.empty((N, 0), device=dev, dtype=torch.float32)
+        ctx.mark_non_differentiable(trans)
+        return weights, features, depth, acc, trans
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dweights, dfeatures, ddepth, dacc, _dtrans):
+        alphas, feats = ctx.saved_tensors
+        N, S = alphas.shape
+        dalphas = torch.empty_like(alphas)
+        need_df = feats is not None and ctx.needs_input_grad[1]
+        dfeats = torch.empty_like(feats) if need_df else None
+        dweights = None if dweights is None else f32c(dweights)
+        dfeatures = None if (dfeatures is None or feats is None) else f32c(dfeatures)
+        ddepth = None if ddepth is None else f32c(ddepth)
+        dacc = None if dacc is None else f32c(dacc)
+        i = ctx.iv.struct()
+        _lib.call("nrb_alpha_composite_bwd", ptr(alphas), ptr(feats), C.byref(i), N, ctx.C, ctx.eps, ctx.sky,
+                                            ptr(dweights), ptr(dfeatures), ptr(ddepth), ptr(dacc), ptr(dalphas),
+                                            ptr(dfeats), stream_ptr())
+        return dalphas, dfeats, None, None, None
+
+
+def alpha_composite(
+    alphas: Tensor, feats: Optional[Tensor], iv: SampleIntervals, trans_eps: float = 0.0, sky_sample: bool = False
+) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """alphas [N,S], feats [N,S,C] -> (weights [N,S], features [N,C], depth [N], accumulation [N])."""
+    return _AlphaComposite.apply(alphas, feats, iv, trans_eps, sky_sample)[:4]
+
+
+def alpha_weights(alphas: Tensor, trans_eps: float = 0.0) -> Tuple[Tensor, Tensor]:
+    """(weights [N,S], transmittance [N,S]) with T_i = prod_{j<i} (1 - alpha_j + eps)."""
+    zeros = torch.zeros((alphas.shape[0], alphas.shape[1] + 1), device=alphas.device, dtype=torch.float32)
+    out = _AlphaComposite.apply(alphas, None, SampleIntervals.from_bins(zeros), trans_eps, False)
+    return out[0], out[4]
+
+
+class _Accumulate(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, weights, values):
+        w = f32c(weights)
+        N, S = w.shape
+        v = None if values is None else f32c(values)
+        Cn = 0 if v is None else v.shape[-1]
+        out = torch.empty((N, max(Cn, 1)), device=w.device, dtype=torch.float32)
+        _lib.call("nrb_accumulate_fwd", ptr(w), ptr(v), N, S, Cn, ptr(out), stream_ptr())
+        ctx.save_for_backward(w, v)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        w, v = ctx.saved_tensors
+        N, S = w.shape
+        dout = f32c(dout)
+        dw = torch.empty_like(w) if ctx.needs_input_grad[0] else None
+        dv = torch.empty_like(v) if (v is not None and ctx.needs_input_grad[1]) else None
+        Cn = 0 if v is None else v.shape[-1]
+        _lib.call("nrb_accumulate_bwd", ptr(w), ptr(v), ptr(dout), N, S, Cn, ptr(dw), ptr(dv), stream_ptr())
+        return dw, dv
+
+
+def accumulate(weights: Tensor, values: Optional[Tensor]) -> Tensor:
+    """sum_s weights[N,S] * values[N,S,C] -> [N,C]  (values None -> [N,1])."""
+    return _Accumulate.apply(weights, values)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused proposal round
+# ------------------------------------------------------------------------------------------------
+class _ProposalRound(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, table, decoder_w, rays: RayData, iv: SampleIntervals, spec: GridSpec, scale: float):
+        table = f32c(table)
+        dec = f32c(decoder_w.reshape(-1))
+        N, S = rays.num_rays, iv.num_samples
+        dev = table.device
+        density = torch.empty((N, S), device=dev, dtype=torch.float32)
+        weights = torch.empty_like(density)
+        train = any(ctx.needs_input_grad[:2])
+        feats = torch.empty((N, S, spec.out_dim), device=dev, dtype=torch.float32) if train else None
+        pre = torch.empty((N, S), device=dev, dtype=torch.float32) if train else None
+        g, r, i = spec.struct(table), rays.struct(), iv.struct()
+        _lib.call("nrb_proposal_fwd", C.byref(r), C.byref(g), ptr(dec), float(scale), C.byref(i), ptr(density),
+                                     ptr(weights), ptr(feats), ptr(pre), stream_ptr())
+        ctx.save_for_backward(table, dec, feats, pre)
+        ctx.rays, ctx.iv, ctx.spec, ctx.scale = rays, iv, spec, float(scale)
+        ctx.dec_shape = decoder_w.shape
+        return density, weights
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, ddensity, dweights):
+        table, dec, feats, pre = ctx.saved_tensors
+        dtable = torch.zeros_like(table)
+        ddec = torch.zeros_like(dec)
+        ddensity = None if ddensity is None else f32c(ddensity)
+        dweights = None if dweights is None else f32c(dweights)
+        g, r, i = ctx.spec.struct(table), ctx.rays.struct(), ctx.iv.struct()
+        _lib.call("nrb_proposal_bwd", C.byref(r), C.byref(g), ptr(dec), ctx.scale, C.byref(i), ptr(feats), ptr(pre),
+                                     ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), stream_ptr())
+        return dtable, ddec.reshape(ctx.dec_shape), None, None, None, None
+
+
+def proposal_round(
+    table: Tensor, decoder_w: Tensor, rays: RayData, iv: SampleIntervals, spec: GridSpec, static_scale: float
+) -> Tuple[Tensor, Tensor]:
+    """One fused proposal round: (density [N,S], weights [N,S])."""
+    return _ProposalRound.apply(table, decoder_w, rays, iv, spec, static_scale)

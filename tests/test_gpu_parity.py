@@ -1,0 +1,470 @@
+"""GPU parity tests: every kernel behind the C ABI against the CPU oracle and the committed golden vectors.
+
+Bars: hash-table rows and searchsorted indices bit-exact at stage level (identical inputs
+-> identical integers); floating-point outputs and gradients within 1e-3 relative of the fp32 reference path (most
+kernels are held to 1e-5 here, the tolerance is written at each assert).
+"""
+import pytest
+import torch
+
+from oracle import neuradar_oracle as O
+from tests.parity_utils import (
+    FixedJitter,
+    build_hot_path,
+    make_ray_bundle,
+    oracle_params,
+    rel_err,
+    run_path_parity,
+    scaled_pixel_area,
+    synthetic_rays,
+)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import neuradar_b200
+
+    assert torch.cuda.is_available()
+    return neuradar_b200
+
+
+def spec_for(nb, L, F, log2T, lo, hi):
+    from neuradar_b200.functional import GridSpec
+
+    return GridSpec(L, F, log2T, tuple(float(s) for s in O.level_scalings(L, lo, hi)))
+
+
+# ------------------------------------------------------------------------------------------------ hash grid
+def test_hash_indices_bit_exact(nb, golden):
+    from neuradar_b200 import functional as Fn
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand((20000, 3), generator=g)
+    x[:4] = torch.tensor([[0.0, 0.0, 0.0], [1.0, 1.0, 1.0], [0.5, 0.25, 0.125], [1.0, 0.0, 0.5]])
+    for (L, lo, hi, log2T) in [(16, 16, 1024, 19), (8, 32, 8192, 22), (6, 128, 4096, 20), (4, 64, 1024, 17)]:
+        spec = spec_for(nb, L, 2, log2T, lo, hi)
+        got = Fn.hash_indices(x.to(DEV), spec).cpu()
+        want, _ = O.hash_corner_indices(x, O.level_scalings(L, lo, hi), log2T)
+        assert got.dtype == torch.int64
+        assert torch.equal(got, want), f"hash rows differ for L={L} T=2^{log2T}"
+    # points outside [0,1] (negative grid coordinates) hash like the reference's int64 arithmetic
+    xo = (torch.rand((4096, 3), generator=g) - 0.5) * 6
+    spec = spec_for(nb, 16, 2, 19, 16, 1024)
+    want, _ = O.hash_corner_indices(xo, O.level_scalings(16, 16, 1024), 19)
+    assert torch.equal(Fn.hash_indices(xo.to(DEV), spec).cpu(), want)
+
+
+@pytest.mark.parametrize("F", [1, 2, 4])
+def test_hash_forward_backward_golden(nb, golden, F):
+    from neuradar_b200 import functional as Fn
+
+    g = golden("hash")
+    spec = spec_for(nb, 16, F, 10, 16, 1024)
+    table = g[f"F{F}_table"].to(DEV).requires_grad_(True)
+    x = g["x"].to(DEV).requires_grad_(True)
+    y = Fn.hash_encode(x, table, spec)
+    assert rel_err(y, g[f"F{F}_y"]) <= 1e-6
+    (y * g[f"F{F}_dy"].to(DEV)).sum().backward()
+    assert rel_err(table.grad, g[f"F{F}_dtable"]) <= 1e-5
+    assert rel_err(x.grad, g[f"F{F}_dx"]) <= 1e-5
+
+
+def test_hash_module_matches_reference_api(nb, golden):
+    g = golden("hash")
+    enc = nb.HashEncoding(num_levels=16, min_res=16, max_res=1024, log2_hashmap_size=10, features_per_level=2).to(DEV)
+    assert torch.equal(enc.scalings.cpu(), g["scalings_A"])
+    assert list(enc.state_dict().keys()) == ["hash_table", "scalings"]
+    with torch.no_grad():
+        enc.hash_table.copy_(g["F2_table"])
+    y = enc(g["x"].to(DEV).view(11, 23, 3))
+    assert y.shape == (11, 23, 32)
+    assert rel_err(y.reshape(-1, 32), g["F2_y"]) <= 1e-6
+    big = nb.HashEncoding(num_levels=8, min_res=32, max_res=8192, log2_hashmap_size=4, features_per_level=4)
+    assert big.scalings[-1].item() == 8191.0
+    # shape-only tests of the reference (tests/field_components/test_encodings.py:142-168)
+    enc2 = nb.HashEncoding(num_levels=4, features_per_level=4, log2_hashmap_size=5).to(DEV)
+    assert enc2(torch.rand((10, 3), device=DEV)).shape == (10, 16)
+    assert enc2.get_out_dim() == 16
+
+
+def test_hash_linearity_full_size(nb):
+    """Size-independent property at BASELINE config-2 size: the encoding is linear in the table."""
+    from neuradar_b200 import functional as Fn
+
+    spec = spec_for(nb, 16, 2, 19, 16, 1024)
+    M = 65536 * 48
+    g = torch.Generator(device=DEV).manual_seed(1)
+    x = torch.rand((M, 3), device=DEV, generator=g)
+    t1 = torch.randn((spec.rows, 2), device=DEV, generator=g)
+    t2 = torch.randn((spec.rows, 2), device=DEV, generator=g)
+    y1, y2 = Fn.hash_encode(x, t1, spec), Fn.hash_encode(x, t2, spec)
+    y12 = Fn.hash_encode(x, 0.5 * t1 - 2.0 * t2, spec)
+    assert float((y12 - (0.5 * y1 - 2.0 * y2)).abs().max()) <= 1e-4
+    # a constant table interpolates to the constant (partition of unity of the trilinear weights)
+    yc = Fn.hash_encode(x, torch.full((spec.rows, 2), 3.0, device=DEV), spec)
+    assert float((yc - 3.0).abs().max()) <= 1e-5
+    # backward is the adjoint of forward: <enc(T), dY> == <T, enc^T(dY)>
+    dy = torch.randn((M, 32), device=DEV, generator=g)
+    t1.requires_grad_(True)
+    (Fn.hash_encode(x, t1, spec) * dy).sum().backward()
+    lhs = (y1.double() * dy.double()).sum()
+    rhs = (t1.detach().double() * t1.grad.double()).sum()
+    assert abs(lhs.item() - rhs.item()) <= 1e-4 * abs(lhs.item())
+
+
+def test_frustum_gaussians(nb):
+    from neuradar_b200 import functional as Fn
+
+    rays = synthetic_rays(512, seed=5)
+    pa = scaled_pixel_area(rays)
+    sb, eb, _ = O.spaced_bins(rays["nears"], rays["fars"].clamp_max(20000.0), 64, None)
+    eb = eb.contiguous()
+    mean, std = O.fast_isotropic_gaussian(rays["origins"], rays["directions"], eb[:, :-1], eb[:, 1:], pa)
+    cmean, cstd = O.contract(mean, std, 100.0)
+    rd = Fn.RayData(rays["origins"].to(DEV), rays["directions"].to(DEV), pa.to(DEV))
+    x, s = Fn.frustum_gaussians(rd, Fn.SampleIntervals.from_bins(eb.to(DEV)), 100.0)
+    assert torch.equal(x.cpu(), cmean.reshape(-1, 3)), "contracted sample means must be bit-exact (they feed the hash)"
+    assert rel_err(s, cstd.reshape(-1)) <= 1e-5
+    # generic Frustums API
+    fr = nb.Frustums(origins=rays["origins"].to(DEV)[:, None, :], directions=rays["directions"].to(DEV)[:, None, :],
+                     starts=eb[:, :-1, None].to(DEV), ends=eb[:, 1:, None].to(DEV), pixel_area=pa.to(DEV)[:, None, :])
+    gs = fr.get_fast_isotropic_gaussian(1, contraction_scale=100.0)
+    assert gs.mean.shape == (512, 64, 1, 3) and torch.equal(gs.mean.reshape(-1, 3), x)
+    world = fr.get_fast_isotropic_gaussian(1)
+    assert rel_err(world.mean, mean[:, :, None, :]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ MLP / SH
+@pytest.mark.parametrize("tag,cfg", [("geo", (32, 2, 32, 33)), ("feat", (48, 3, 32, 32)), ("lidar", (48, 3, 32, 2)),
+                                     ("radar", (48, 3, 16, 3))])
+def test_mlp_golden(nb, golden, tag, cfg):
+    g = golden("kats")
+    i, n, w, o = cfg
+    m = nb.MLP(in_dim=i, num_layers=n, layer_width=w, out_dim=o).to(DEV)
+    assert [k for k in m.state_dict()] == [f"layers.{k}.{p}" for k in range(n) for p in ("weight", "bias")]
+    with torch.no_grad():
+        for k, layer in enumerate(m.layers):
+            layer.weight.copy_(g[f"mlp_{tag}_w{k}"])
+            layer.bias.copy_(g[f"mlp_{tag}_b{k}"])
+    x = g[f"mlp_{tag}_x"].to(DEV).requires_grad_(True)
+    y = m(x)
+    assert rel_err(y, g[f"mlp_{tag}_y"]) <= 1e-5
+    (y * g[f"mlp_{tag}_dy"].to(DEV)).sum().backward()
+    assert rel_err(x.grad, g[f"mlp_{tag}_dx"]) <= 1e-5
+    for k, layer in enumerate(m.layers):
+        assert rel_err(layer.weight.grad, g[f"mlp_{tag}_dw{k}"]) <= 1e-5
+        assert rel_err(layer.bias.grad, g[f"mlp_{tag}_db{k}"]) <= 1e-5
+
+
+def test_mlp_many_tiles_and_ragged(nb):
+    torch.manual_seed(0)
+    m = nb.MLP(in_dim=32, num_layers=2, layer_width=32, out_dim=33).to(DEV)
+    for M in (1, 127, 128, 129, 100003):
+        x = torch.randn((M, 32), device=DEV, requires_grad=True)
+        y = m(x)
+        xr = x.detach().cpu().requires_grad_(True)
+        ws = [l.weight.detach().cpu().requires_grad_(True) for l in m.layers]
+        bs = [l.bias.detach().cpu().requires_grad_(True) for l in m.layers]
+        yr = O.mlp(xr, ws, bs)
+        assert rel_err(y, yr) <= 1e-5
+        dy = torch.randn_like(yr)
+        m.zero_grad()
+        (y * dy.to(DEV)).sum().backward()
+        (yr * dy).sum().backward()
+        assert rel_err(x.grad, xr.grad) <= 1e-5
+        assert rel_err(m.layers[0].weight.grad, ws[0].grad) <= 2e-5
+        assert rel_err(m.layers[1].bias.grad, bs[1].grad) <= 2e-5
+    assert m(torch.empty((0, 32), device=DEV)).shape == (0, 33)
+
+
+def test_sh16(nb, golden):
+    from neuradar_b200 import functional as Fn
+
+    g = golden("kats")
+    assert rel_err(Fn.sh16(g["sh_dirs"].to(DEV), normalize_to_unit_cube=True), g["sh_out"]) <= 1e-6
+    enc = nb.SHEncoding(levels=4)
+    assert rel_err(enc(g["sh_dirs"].to(DEV)), g["sh_enc"]) <= 1e-6
+
+
+# ------------------------------------------------------------------------------------------------ samplers
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_samplers_golden(nb, golden, mode):
+    from neuradar_b200 import functional as Fn
+
+    g = golden("samplers")
+    N = 96
+    rd = Fn.RayData(torch.zeros((N, 3), device=DEV), torch.ones((N, 3), device=DEV), torch.ones((N,), device=DEV),
+                    g["nears"].to(DEV), g["fars"].to(DEV))
+    j0 = g[f"{mode}_j0"].to(DEV) if mode == "train" else None
+    j1 = g[f"{mode}_j1"].to(DEV) if mode == "train" else None
+    sb0, eb0 = Fn.spaced_bins(rd, 64, j0, -1.0, 0.1)
+    assert torch.equal(sb0.cpu(), g[f"{mode}_sbins0"]), "initial spacing bins must be bit-exact"
+    assert torch.equal(eb0.cpu(), g[f"{mode}_ebins0"]), "initial euclidean bins must be bit-exact"
+    w = g[f"{mode}_w"][..., 0].to(DEV)
+    sb1, eb1, inds, cdf = Fn.pdf_sample(rd, w, sb0, 48, j1, -1.0, 0.1, return_debug=True)
+    # stage-level exactness: the kernel's indices are torch.searchsorted of the kernel's own cdf and the exact u
+    u = O.pdf_u(N, 48, None if j1 is None else j1.cpu())
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu().contiguous(), u, side="right"))
+    # and the cdf / indices / bins agree with the reference's
+    ref_cdf = O.pdf_cdf(g[f"{mode}_w"][..., 0])
+    assert float((cdf.cpu() - ref_cdf).abs().max()) <= 2e-7
+    ref_bins, ref_inds = O.pdf_invert(ref_cdf, u, g[f"{mode}_sbins0"])
+    assert float((inds.cpu() != ref_inds).float().mean()) <= 1e-3
+    assert float((sb1.cpu() - g[f"{mode}_sbins1"]).abs().max()) <= 1e-6
+    assert rel_err(eb1, g[f"{mode}_ebins1"]) <= 1e-5
+    assert bool((sb1[:, 1:] >= sb1[:, :-1]).all()), "sampled bins must be sorted"
+
+
+def test_pdf_sampler_known_answer(nb, golden):
+    from neuradar_b200 import functional as Fn
+
+    g = golden("samplers")
+    rd = Fn.RayData(torch.zeros((2, 3), device=DEV), torch.ones((2, 3), device=DEV), torch.ones((2,), device=DEV),
+                    torch.full((2,), 2.0, device=DEV), torch.full((2,), 6.0, device=DEV))
+    sb, eb = Fn.pdf_sample(rd, g["kat_w"][..., 0].to(DEV), g["kat_in_sbins"].to(DEV), 4, None, -1.0, 0.1)
+    assert float((sb.cpu() - g["kat_sbins"]).abs().max()) <= 1e-7
+    torch.testing.assert_close(sb.cpu()[1], torch.tensor([0.1, 0.3, 0.5, 0.7, 0.9]), rtol=1e-6, atol=1e-7)
+
+
+def test_sampler_modules(nb):
+    rays = synthetic_rays(300, seed=8)
+    rb = make_ray_bundle(rays, DEV)
+    rb.fars.clamp_max_(20000.0)
+    ps = nb.PowerSampler(lambda_=-1.0, scaling=0.1)
+    ps.eval()
+    rs = ps(rb, num_samples=64)
+    assert rs.shape == (300, 64)
+    assert rs.frustums.origins.shape == (300, 64, 3) and rs.frustums.origins.stride(1) == 0
+    assert rs.frustums.starts.shape == (300, 64, 1) and rs.deltas.shape == (300, 64, 1)
+    eb = torch.cat([rs.frustums.starts[..., 0], rs.frustums.ends[..., -1:, 0]], -1)
+    assert rel_err(rs.spacing_to_euclidean_fn(rs.spacing_bins), eb) <= 1e-5
+    pdf = nb.PDFSampler(include_original=False, single_jitter=True)
+    pdf.eval()
+    rs2 = pdf(rb, rs, torch.rand((300, 64, 1), device=DEV), num_samples=48)
+    assert rs2.shape == (300, 48)
+    assert bool((rs2.frustums.ends >= rs2.frustums.starts).all())
+    # reference test: "just check that it doesn't crash" + sample count (tests/model_components/test_ray_sampler.py)
+    assert rs2.frustums.get_positions().shape == (300, 48, 3)
+
+
+# ------------------------------------------------------------------------------------------------ compositing
+def test_density_weights_golden(nb, golden):
+    from neuradar_b200 import functional as Fn
+
+    g = golden("kats")
+    bins = g["gw_bins"].to(DEV)
+    dens = g["gw_dens"][..., 0].to(DEV).requires_grad_(True)
+    w = Fn.density_weights(dens, Fn.SampleIntervals.from_bins(bins))
+    ref = g["gw_w"][..., 0]
+    finite = torch.isfinite(ref)
+    assert rel_err(w.cpu()[finite], ref[finite]) <= 1e-5
+    (w * g["gw_dw"][..., 0].to(DEV)).sum().backward()
+    gref = g["gw_ddens"][..., 0]
+    ok = torch.isfinite(gref) & (g["gw_dens"][..., 0] < 1e20)
+    assert rel_err(dens.grad.cpu()[ok], gref[ok]) <= 1e-4
+    kat = Fn.density_weights(torch.tensor([[1.0, 2.0, 0.5, 3.0]], device=DEV),
+                             Fn.SampleIntervals.from_bins(torch.tensor([[0.0, 0.5, 1.0, 2.0, 3.0]], device=DEV)))
+    torch.testing.assert_close(kat.cpu()[0], torch.tensor([0.39346933, 0.3834005, 0.08779488, 0.12859733]), rtol=1e-6, atol=0)
+
+
+def test_ray_samples_weight_api(nb, golden):
+    g = golden("kats")
+    w, T = nb.RaySamples.get_weights_and_transmittance_from_alphas(g["alpha2_in"].to(DEV))
+    assert w.shape == (37, 48, 1) and T.shape == (37, 49, 1)
+    assert rel_err(w, g["alpha2_w"]) <= 1e-5
+    assert rel_err(T, g["alpha2_T"]) <= 1e-5
+    w1 = nb.RaySamples.get_weights_and_transmittance_from_alphas(g["alpha_in"].to(DEV), weights_only=True)
+    torch.testing.assert_close(w1.cpu().flatten(), torch.tensor([0.1, 0.45000005, 0.40500015, 0.0090000136]), rtol=1e-6, atol=0)
+    from neuradar_b200 import nerfacc_compat
+
+    wn, tn = nerfacc_compat.render_weight_from_alpha(g["alpha2_in"][..., 0].to(DEV))
+    w0, t0 = O.alpha_weights(g["alpha2_in"][..., 0], eps=0.0)
+    assert rel_err(wn, w0) <= 1e-5 and rel_err(tn, t0[:, :-1]) <= 1e-5
+
+
+def test_renderers_golden(nb, golden):
+    g = golden("kats")
+    bins = g["gw_bins"].to(DEV)
+    rb = nb.RayBundle(origins=torch.zeros((37, 3), device=DEV), directions=torch.ones((37, 3), device=DEV),
+                      pixel_area=torch.ones((37, 1), device=DEV))
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    feats, w = g["rend_feats"].to(DEV), g["rend_w"].to(DEV)
+    assert rel_err(nb.FeatureRenderer()(features=feats, weights=w), g["rend_feature"]) <= 1e-5
+    assert rel_err(nb.AccumulationRenderer()(weights=w), g["rend_acc"]) <= 1e-5
+    assert rel_err(nb.DepthRenderer(method="expected")(weights=w, ray_samples=rs), g["rend_depth_expected"]) <= 1e-5
+    assert rel_err(nb.DepthRenderer(method="median")(weights=w * 3, ray_samples=rs), g["rend_depth_median"]) <= 1e-6
+    # the reference's renderer tests use loose inequalities (tests/model_components/test_renderers.py)
+    acc = nb.AccumulationRenderer()(weights=torch.ones((3, 5, 1), device=DEV))
+    assert bool((acc > 0.9).all())
+
+
+@pytest.mark.parametrize("eps", [0.0, 1e-7])
+@pytest.mark.parametrize("S", [48, 128, 33])
+def test_alpha_composite_forward_backward(nb, eps, S):
+    from neuradar_b200 import functional as Fn
+
+    g = torch.Generator().manual_seed(S)
+    N, C = 257, 32
+    alphas = torch.rand((N, S), generator=g) ** 3
+    alphas[0] = 0.0
+    alphas[1, 5] = 1.0  # opaque sample: later transmittance is exactly 0 when eps == 0
+    alphas[2] = 1.0
+    feats = torch.randn((N, S, C), generator=g)
+    bins = torch.cumsum(torch.rand((N, S + 1), generator=g), dim=-1)
+    a_ref = alphas.clone().requires_grad_(True)
+    f_ref = feats.clone().requires_grad_(True)
+    ref = O.composite(a_ref, f_ref, bins[:, :-1], bins[:, 1:], eps)
+    a = alphas.to(DEV).requires_grad_(True)
+    f = feats.to(DEV).requires_grad_(True)
+    w, feat, depth, acc = Fn.alpha_composite(a, f, Fn.SampleIntervals.from_bins(bins.to(DEV)), eps, True)
+    assert rel_err(feat, ref["features"]) <= 1e-5
+    assert rel_err(depth, ref["depth"][:, 0]) <= 1e-5
+    assert rel_err(acc, ref["accumulation"][:, 0]) <= 1e-5
+    assert rel_err(w[:, :-1], ref["weights"][..., 0]) <= 1e-5
+    gw = torch.randn((N, S - 1), generator=g)
+    gf = torch.randn((N, C), generator=g)
+    gd = torch.randn((N,), generator=g)
+    ga = torch.randn((N,), generator=g)
+    loss = (w[:, :-1] * gw.to(DEV)).sum() + (feat * gf.to(DEV)).sum() + (depth * gd.to(DEV)).sum() + (acc * ga.to(DEV)).sum()
+    loss.backward()
+    lref = (ref["weights"][..., 0] * gw).sum() + (ref["features"] * gf).sum() + (ref["depth"][:, 0] * gd).sum() \
+        + (ref["accumulation"][:, 0] * ga).sum()
+    lref.backward()
+    assert rel_err(f.grad, f_ref.grad) <= 1e-5
+    assert rel_err(a.grad, a_ref.grad) <= 1e-4
+
+
+# ------------------------------------------------------------------------------------------------ fields / whole path
+def test_proposal_round_vs_oracle(nb):
+    model = build_hot_path(log2_main=12, log2_prop=14, table_gain=(300.0, 2000.0), seed=4, device=DEV)
+    rays = synthetic_rays(384, seed=6)
+    pa = scaled_pixel_area(rays)
+    _, eb, _ = O.spaced_bins(rays["nears"], rays["fars"].clamp_max(20000.0), 64, torch.rand((384, 65)))
+    eb = eb.contiguous()
+    fld, props = oracle_params(model)
+    p = props[1]
+    dens_ref = O.proposal_density(p, rays["origins"], rays["directions"], pa, eb[:, :-1], eb[:, 1:])
+    w_ref = O.density_weights(dens_ref, (eb[:, 1:] - eb[:, :-1])[..., None])
+    from neuradar_b200 import functional as Fn
+
+    rd = Fn.RayData(rays["origins"].to(DEV), rays["directions"].to(DEV), pa.to(DEV))
+    pf = model.proposal_fields[1]
+    dens, w = Fn.proposal_round(pf.hashgrid.static_grid.hash_table, pf.density_decoder.weight, rd,
+                                Fn.SampleIntervals.from_bins(eb.to(DEV)), pf.hashgrid.static_grid.spec, 100.0)
+    assert rel_err(dens, dens_ref[..., 0]) <= 1e-4
+    assert rel_err(w, w_ref[..., 0]) <= 1e-4
+    gw = torch.randn((384, 64))
+    (w * gw.to(DEV)).sum().backward()
+    (w_ref[..., 0] * gw).sum().backward()
+    assert rel_err(pf.hashgrid.static_grid.hash_table.grad, p.grid.table.grad) <= 1e-3
+    assert rel_err(pf.density_decoder.weight.grad, p.decoder_w.grad) <= 1e-3
+    # the unfused API (get_density + RaySamples.get_weights) gives the same numbers
+    rb = make_ray_bundle(rays, DEV)
+    rb.pixel_area = pa.to(DEV)
+    rs = rb.get_ray_samples(bin_starts=eb[:, :-1, None].to(DEV), bin_ends=eb[:, 1:, None].to(DEV))
+    d2, _ = pf.get_density(rs)
+    assert d2.shape == (384, 64, 1) and rel_err(d2, dens_ref) <= 1e-4
+    assert rel_err(rs.get_weights(d2), w_ref) <= 1e-4
+
+
+def test_field_forward_vs_oracle(nb):
+    model = build_hot_path(log2_main=14, log2_prop=12, table_gain=(300.0, 2000.0), seed=9, device=DEV)
+    rays = synthetic_rays(320, seed=10)
+    pa = scaled_pixel_area(rays)
+    _, eb, _ = O.spaced_bins(rays["nears"], rays["fars"].clamp_max(20000.0), 48, torch.rand((320, 49)))
+    eb = eb.contiguous()
+    fld, _ = oracle_params(model)
+    ref = O.field_forward(fld, rays["origins"], rays["directions"], pa, eb[:, :-1], eb[:, 1:])
+    rb = make_ray_bundle(rays, DEV)
+    rb.pixel_area = pa.to(DEV)
+    rs = rb.get_ray_samples(bin_starts=eb[:, :-1, None].to(DEV), bin_ends=eb[:, 1:, None].to(DEV))
+    out = model.field(rs)
+    assert out[nb.FieldHeadNames.FEATURE].shape == (320, 48, 32)
+    assert rel_err(out[nb.FieldHeadNames.FEATURE], ref["feature"]) <= 1e-4
+    assert rel_err(out[nb.FieldHeadNames.SDF], ref["sdf"]) <= 1e-4
+    assert float((out[nb.FieldHeadNames.ALPHA].cpu() - ref["alpha"]).abs().max()) <= 1e-4
+
+
+@pytest.mark.parametrize("train", [True, False])
+def test_whole_path_vs_oracle(nb, train):
+    report = run_path_parity(num_rays=512, device=DEV, seed=11, train=train)
+    assert report["ok"], report
+
+
+@pytest.mark.parametrize("mode", ["train", "eval"])
+def test_whole_path_golden(nb, golden, mode):
+    """The path on the reference's own outputs (tests/golden/path.npz, made by running the reference)."""
+    g = golden("path")
+    model = build_hot_path(log2_main=10, log2_prop=10, late_binding=False, device=DEV)
+    sd = {"field.hashgrid.static_grid.hash_table": g["main_table"], "field.sdf_to_density.beta": g["beta"]}
+    for k in range(2):
+        sd[f"field.mlp_geo.layers.{k}.weight"], sd[f"field.mlp_geo.layers.{k}.bias"] = g[f"geo_w{k}"], g[f"geo_b{k}"]
+    for k in range(3):
+        sd[f"field.mlp_feature.layers.{k}.weight"], sd[f"field.mlp_feature.layers.{k}.bias"] = g[f"feat_w{k}"], g[f"feat_b{k}"]
+    for i in range(2):
+        sd[f"proposal_fields.{i}.hashgrid.static_grid.hash_table"] = g[f"prop{i}_table"]
+        sd[f"proposal_fields.{i}.density_decoder.weight"] = g[f"prop{i}_w"]
+    missing = model.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all(k.endswith(("scalings", "beta_min")) for k in missing.missing_keys)
+    model.train(mode == "train")
+    N = 64
+    rb = nb.RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=g["pixel_area"].to(DEV),
+                      nears=g["nears"].to(DEV), fars=g["fars"].to(DEV), times=g["times"].to(DEV), metadata={})
+    pre = mode + "_"
+    # golden rays were generated without the x9 camera scaling: bypass _scale_pixel_area
+    model._scale_pixel_area = lambda bundle: None
+    if mode == "train":
+        with FixedJitter([g[f"{pre}jitter{i}"] for i in range(3)]):
+            out = model(rb)
+    else:
+        with torch.no_grad():
+            out = model(rb)
+    # the golden composite uses the in-tree 1e-7 formula; the model uses nerfacc's (eps=0): <=6e-6 apart
+    assert rel_err(out["features"], g[f"{pre}features"]) <= 1e-3
+    assert rel_err(out["depth"], g[f"{pre}depth"]) <= 1e-3
+    assert rel_err(out["accumulation"], g[f"{pre}accumulation"]) <= 1e-3
+    if mode == "train":
+        for i in range(2):
+            assert rel_err(out["weights_list"][i], g[f"{pre}prop_w{i}"]) <= 1e-3
+            rs = out["ray_samples_list"][i]
+            assert float((rs.spacing_bins.cpu() - g[f"{pre}sbins{i}"]).abs().max()) <= 2e-6
+        assert rel_err(out["weights_list"][2], g[f"{pre}weights"]) <= 1e-3
+        nb.bench_loss(out).backward()
+        assert rel_err(model.field.hashgrid.static_grid.hash_table.grad, g[f"{pre}d_main_table"]) <= 1e-3
+        for k in range(2):
+            assert rel_err(model.field.mlp_geo.layers[k].weight.grad, g[f"{pre}d_geo_w{k}"]) <= 1e-3
+        for k in range(3):
+            assert rel_err(model.field.mlp_feature.layers[k].weight.grad, g[f"{pre}d_feat_w{k}"]) <= 1e-3
+            assert rel_err(model.field.mlp_feature.layers[k].bias.grad, g[f"{pre}d_feat_b{k}"]) <= 1e-3
+        assert rel_err(model.field.sdf_to_density.beta.grad, g[f"{pre}d_beta"]) <= 1e-3
+        for i in range(2):
+            assert rel_err(model.proposal_fields[i].hashgrid.static_grid.hash_table.grad, g[f"{pre}d_prop{i}_table"]) <= 1e-3
+            assert rel_err(model.proposal_fields[i].density_decoder.weight.grad, g[f"{pre}d_prop{i}_w"]) <= 1e-3
+
+
+def test_full_size_properties(nb):
+    """BASELINE config 2 (65536 mixed rays, 2^19 main table, 48 samples): size-independent invariants."""
+    model = build_hot_path(device=DEV)  # cfg-A main grid, cfg-P proposals, (64,48)/48 samples
+    model.train()
+    rays = synthetic_rays(65536, seed=42)
+    out = model(make_ray_bundle(rays, DEV))
+    acc = out["accumulation"]
+    assert out["features"].shape == (65536, 32) and out["depth"].shape == (65536, 1)
+    assert bool(torch.isfinite(out["features"]).all()) and bool(torch.isfinite(out["depth"]).all())
+    assert float(acc.min()) >= 0.0 and float(acc.max()) <= 1.0 + 1e-5
+    for w in out["weights_list"]:
+        assert float(w.min()) >= 0.0 and float(w.sum(dim=1).max()) <= 1.0 + 1e-4
+    for rs in out["ray_samples_list"][:2]:
+        eb = rs.euclidean_bins
+        assert bool((eb[:, 1:] >= eb[:, :-1]).all()) and float(eb.min()) >= 0.0 and float(eb.max()) <= 20000.0 * (1 + 1e-5)
+    nb.bench_loss(out).backward()
+    for name, p in model.named_parameters():
+        if name.startswith("proposal_fields.0"):
+            assert p.grad is None  # never evaluated (late-binding density_fns)
+        else:
+            assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
+    assert float(model.field.hashgrid.static_grid.hash_table.grad.abs().sum()) > 0

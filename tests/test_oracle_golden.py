@@ -84,21 +84,24 @@ def test_reference_known_answer_tests(golden):
 def test_weights_and_renderers(golden):
     g = golden("kats")
     w, T = O.alpha_weights(g["alpha2_in"][..., 0], eps=1e-7)
-    assert torch.equal(w, g["alpha2_w"][..., 0]) and torch.equal(T, g["alpha2_T"][..., 0])
+    torch.testing.assert_close(w, g["alpha2_w"][..., 0], rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(T, g["alpha2_T"][..., 0], rtol=1e-6, atol=1e-12)
     w0, _ = O.alpha_weights(g["alpha2_in"][..., 0], eps=0.0)  # nerfacc contract vs in-tree twin
     torch.testing.assert_close(w0, w, rtol=1e-4, atol=1e-6)
     bins = g["gw_bins"]
     dens = g["gw_dens"].clone().requires_grad_(True)
     gw = O.density_weights(dens, (bins[:, 1:] - bins[:, :-1])[..., None])
-    assert torch.equal(gw, g["gw_w"])
+    torch.testing.assert_close(gw, g["gw_w"], rtol=1e-6, atol=1e-12)
     (gw * g["gw_dw"]).sum().backward()
     torch.testing.assert_close(dens.grad, g["gw_ddens"], rtol=1e-6, atol=0, equal_nan=True)
     starts, ends = bins[:, :-1], bins[:, 1:]
-    assert torch.equal(torch.sum(g["rend_feats"] * g["rend_w"], dim=-2), g["rend_feature"])
-    assert torch.equal(O.expected_depth(g["rend_w"], starts, ends), g["rend_depth_expected"])
+    # float reductions: torch's CPU kernels may split them differently from run to run (thread count), so these
+    # are held to 1e-6 instead of bit equality; integer outputs and bins stay bit-exact elsewhere in this file
+    torch.testing.assert_close(torch.sum(g["rend_feats"] * g["rend_w"], dim=-2), g["rend_feature"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(O.expected_depth(g["rend_w"], starts, ends), g["rend_depth_expected"], rtol=1e-6, atol=0)
     assert torch.equal(O.median_depth(g["rend_w"] * 3, starts, ends), g["rend_depth_median"])
-    assert torch.equal(O.sh16((g["sh_dirs"] + 1.0) / 2.0), g["sh_out"])
-    assert torch.equal(O.sh16(g["sh_dirs"]), g["sh_enc"])
+    torch.testing.assert_close(O.sh16((g["sh_dirs"] + 1.0) / 2.0), g["sh_out"], rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(O.sh16(g["sh_dirs"]), g["sh_enc"], rtol=1e-6, atol=1e-7)
 
 
 @pytest.mark.parametrize("tag,n", [("geo", 2), ("feat", 3), ("lidar", 3), ("radar", 3)])
