@@ -154,6 +154,7 @@ class KernelTimer:
 
 
 TIMER: Optional[KernelTimer] = None
+_EMPTY_SENTINEL = 256  # non-null, 16-byte aligned, never dereferenced (only passed together with a zero size)
 
 
 def call(name: str, *args, tag: Optional[str] = None) -> None:
@@ -191,6 +192,8 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
         raise NeuradarB200Error("neuradar_b200 ops need CUDA tensors; there is no CPU path")
     if not t.is_contiguous():
         raise NeuradarB200Error("internal error: non-contiguous tensor reached the C ABI")
+    if t.numel() == 0:
+        return _EMPTY_SENTINEL  # empty tensors have a null data_ptr; sizes of 0 make every entry point a no-op
     return t.data_ptr()
 
 

@@ -1,0 +1,43 @@
+"""GPU probe: time hash fwd/bwd per level resolution and atomics flavours (scratch tool, not part of the product)."""
+import sys, os, torch
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import neuradar_b200 as nb
+from neuradar_b200 import functional as F
+from tests.parity_utils import synthetic_rays, scaled_pixel_area, build_hot_path, make_ray_bundle
+
+dev = "cuda"
+model = build_hot_path(device=dev)
+model.eval()
+rays = synthetic_rays(65536, seed=42)
+with torch.no_grad():
+    out_rs = model._get_ray_samples(make_ray_bundle(rays, dev))[0]
+rd, iv = out_rs.per_ray()
+x, std = F.frustum_gaussians(rd, iv, 100.0)
+M = x.shape[0]
+print("M", M, "x range", float(x.min()), float(x.max()))
+
+def timeit(fn, n=5):
+    for _ in range(2): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+for Fdim in (1, 2, 4):
+    for res in (16, 27, 48, 84, 147, 256, 445, 1024):
+        enc = nb.HashEncoding(num_levels=1, min_res=res, max_res=res, log2_hashmap_size=19, features_per_level=Fdim).to(dev)
+        spec = enc.spec
+        table = enc.hash_table.detach()
+        dy = torch.randn((M, Fdim), device=dev)
+        dtable = torch.zeros_like(table)
+        import ctypes as C
+        from neuradar_b200 import _lib
+        g = spec.struct(table)
+        def fwd():
+            out = torch.empty((M, Fdim), device=dev)
+            _lib.call("nrb_hash_fwd", C.byref(g), x.data_ptr(), std.data_ptr(), out.data_ptr(), M, _lib.stream_ptr())
+        def bwd():
+            _lib.call("nrb_hash_bwd", C.byref(g), x.data_ptr(), std.data_ptr(), dy.data_ptr(), dtable.data_ptr(), None, M, _lib.stream_ptr())
+        print(f"F={Fdim} res={res:5d}  fwd {timeit(fwd):7.3f} ms   bwd {timeit(bwd):7.3f} ms  ({M*8/1e6:.0f}M atomics)")
