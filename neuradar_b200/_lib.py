@@ -84,7 +84,7 @@ SIGNATURES = {
     "nrb_launch_count": [],
     "nrb_hash_fwd": [C.POINTER(Grid), _P, _P, _P, _I64, _P],
     "nrb_hash_indices": [C.POINTER(Grid), _P, _P, _I64, _P],
-    "nrb_hash_bwd": [C.POINTER(Grid), _P, _P, _P, _P, _P, _I64, _P],
+    "nrb_hash_bwd": [C.POINTER(Grid), _P, _P, _P, _P, _P, _I64, _I32, _P],
     "nrb_frustum_gaussians": [C.POINTER(Rays), C.POINTER(Intervals), _F, _P, _P, _P],
     "nrb_mlp_fwd": [C.POINTER(Mlp), _P, _P, _P, _I64, _P],
     "nrb_mlp_bwd": [C.POINTER(Mlp), _P, _P, _P, _P, C.POINTER(MlpGrad), _I64, _P],

@@ -81,7 +81,9 @@ __global__ void __launch_bounds__(kRayWarps * 32) density_weights_bwd_kernel(con
         const float v = __shfl_down_sync(kFull, incl, o);
         if (lane + o < 32) incl += v;
       }
-      const float later = suffix + (incl - gw);
+      float excl = __shfl_down_sync(kFull, incl, 1);
+      if (lane == 31) excl = 0.0f;
+      const float later = suffix + excl;
       if (ok) ddens[n * S + i] = (g * trans[c] * e - later) * delta[c];
       suffix += __shfl_sync(kFull, incl, 0);
     }
@@ -222,7 +224,9 @@ __global__ void __launch_bounds__(kRayWarps * 32) alpha_composite_bwd_kernel(
       const float v = __shfl_down_sync(kFull, incl, o);
       if (lane + o < 32) incl += v;
     }
-    const float later = suffix + (incl - gw);
+    float excl = __shfl_down_sync(kFull, incl, 1);
+      if (lane == 31) excl = 0.0f;
+      const float later = suffix + excl;
     if (ok) {
       const float om = add(sub(1.0f, a), eps);
       float tail;

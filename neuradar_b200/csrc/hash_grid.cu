@@ -6,6 +6,8 @@
 // are hit at random, so there is nothing to coalesce on the gather side; what can be coalesced is the [M, L*F]
 // feature matrix, and with the level fastest a warp writes (reads, in the backward pass) one contiguous
 // 32*F*4-byte span of it.  Each thread issues its 8 independent F-wide vector gathers before touching any of them.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace nrb {
@@ -81,20 +83,23 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ base, uint32_t r
   }
 }
 
+// Levels [level0, L) with plain vector reductions into the table (levels below level0 are handled by the
+// shared-memory privatised kernel further down).
 template <int F, bool kNeedDx>
 __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
                                                        const float* __restrict__ std, const float* __restrict__ dy,
                                                        float* __restrict__ dtable, float* __restrict__ dx,
-                                                       int64_t total) {
+                                                       int64_t total, int level0) {
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int64_t m = gid / g.num_levels;
-  const int l = static_cast<int>(gid - m * g.num_levels);
+  const int nl = g.num_levels - level0;
+  const int64_t m = gid / nl;
+  const int l = level0 + static_cast<int>(gid - m * nl);
   const float scal = g.scalings[l];
   const Cell c = locate_cell(__ldg(x + 3 * m), __ldg(x + 3 * m + 1), __ldg(x + 3 * m + 2), scal,
                              (1u << g.log2_size) - 1u);
   using V = typename Feat<F>::type;
-  const V gv = __ldg(reinterpret_cast<const V*>(dy) + gid);
+  const V gv = __ldg(reinterpret_cast<const V*>(dy) + m * g.num_levels + l);
   float gr[F];
   if constexpr (F == 1) {
     gr[0] = gv;
@@ -138,6 +143,97 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ G
   corner_weights(c, w);
 #pragma unroll
   for (int k = 0; k < 8; ++k) scatter_row<F>(dtable + level_off, c.row[k], gr, w[k]);
+}
+
+// Coarse levels: a level whose dense vertex lattice (res+1)^3 x F floats fits in shared memory is accumulated there
+// first.  Millions of samples fall on a few thousand table rows at these levels, and same-row float reductions
+// serialise in L2 (measured: 25 M reductions on the 4913 rows of a res-16 level take 7 ms, on a res-1024 level
+// 0.16 ms).  Each CTA privatises the lattice, consumes a contiguous chunk of samples (walked ray-fastest so that the
+// lanes of a warp sit in different cells) and flushes each touched vertex with ONE reduction to its hashed row.
+constexpr int kDenseThreads = 512;
+constexpr int kDenseMaxBytes = 200 * 1024;
+
+template <int F>
+__global__ void __launch_bounds__(kDenseThreads) hash_bwd_dense_kernel(
+    const __grid_constant__ GridDev g, int level, const float* __restrict__ x, const float* __restrict__ std,
+    const float* __restrict__ dy, float* __restrict__ dtable, int64_t M, int group, int64_t chunk) {
+  extern __shared__ __align__(16) float acc[];
+  const float scal = g.scalings[level];
+  const int R1 = static_cast<int>(scal) + 1;
+  const int V = R1 * R1 * R1;
+  for (int i = threadIdx.x; i < V * F; i += kDenseThreads) acc[i] = 0.0f;
+  __syncthreads();
+  const uint32_t mask = (1u << g.log2_size) - 1u;
+  float* level_base = dtable + (static_cast<size_t>(level) << g.log2_size) * F;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * chunk;
+  const int count = static_cast<int>(min(chunk, M - m0));
+  const int nr = (count % group == 0) ? count / group : count;  // rays in this chunk (whole rays when possible)
+  const int ns = (count % group == 0) ? group : 1;
+  for (int idx = threadIdx.x; idx < count; idx += kDenseThreads) {
+    const int s = idx / nr, r = idx - s * nr;
+    const int64_t m = m0 + static_cast<int64_t>(r) * ns + s;
+    const float px = __ldg(x + 3 * m), py = __ldg(x + 3 * m + 1), pz = __ldg(x + 3 * m + 2);
+    using Vt = typename Feat<F>::type;
+    const Vt gv = __ldg(reinterpret_cast<const Vt*>(dy) + m * g.num_levels + level);
+    float gr[F];
+    if constexpr (F == 1) {
+      gr[0] = gv;
+    } else if constexpr (F == 2) {
+      gr[0] = gv.x;
+      gr[1] = gv.y;
+    } else {
+      gr[0] = gv.x;
+      gr[1] = gv.y;
+      gr[2] = gv.z;
+      gr[3] = gv.w;
+    }
+    if (std != nullptr) {
+      const float lw = level_weight(scal, __ldg(std + m));
+#pragma unroll
+      for (int j = 0; j < F; ++j) gr[j] *= lw;
+    }
+    const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const int xf = static_cast<int>(fx), yf = static_cast<int>(fy), zf = static_cast<int>(fz);
+    const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
+    Cell c;
+    c.ox = sub(sx, fx);
+    c.oy = sub(sy, fy);
+    c.oz = sub(sz, fz);
+    float w[8];
+    corner_weights(c, w);
+    const bool inside = xf >= 0 && yf >= 0 && zf >= 0 && xc < R1 && yc < R1 && zc < R1;
+    const int cx[8] = {xc, xc, xf, xf, xc, xc, xf, xf};
+    const int cy[8] = {yc, yf, yf, yc, yc, yf, yf, yc};
+    const int cz[8] = {zc, zc, zc, zc, zf, zf, zf, zf};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      if (inside) {
+        float* p = acc + ((cz[k] * R1 + cy[k]) * R1 + cx[k]) * F;
+#pragma unroll
+        for (int j = 0; j < F; ++j) atomicAdd(p + j, gr[j] * w[k]);
+      } else {  // points outside the unit cube: straight to the hashed row
+        const uint32_t row = (static_cast<uint32_t>(cx[k]) ^ (static_cast<uint32_t>(cy[k]) * kPrimeY) ^
+                              (static_cast<uint32_t>(cz[k]) * kPrimeZ)) & mask;
+        scatter_row<F>(level_base, row, gr, w[k]);
+      }
+    }
+  }
+  __syncthreads();
+  for (int v = threadIdx.x; v < V; v += kDenseThreads) {
+    float val[F];
+    bool any = false;
+#pragma unroll
+    for (int j = 0; j < F; ++j) {
+      val[j] = acc[v * F + j];
+      any |= (val[j] != 0.0f);
+    }
+    if (!any) continue;
+    const int ix = v % R1, iy = (v / R1) % R1, iz = v / (R1 * R1);
+    const uint32_t row = (static_cast<uint32_t>(ix) ^ (static_cast<uint32_t>(iy) * kPrimeY) ^
+                          (static_cast<uint32_t>(iz) * kPrimeZ)) & mask;
+    scatter_row<F>(level_base, row, val, 1.0f);
+  }
 }
 
 __global__ void __launch_bounds__(256) frustum_gaussians_kernel(const float* __restrict__ origins,
@@ -193,32 +289,65 @@ extern "C" int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t*
   return finish_launch("nrb_hash_indices");
 }
 
+template <int F>
+static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float* x, const float* std, const float* dy,
+                           float* dtable, float* dx, int64_t M, int group, cudaStream_t s) {
+  // dense-privatised coarse levels (not used when the input gradient is requested: that path needs the features)
+  int level0 = 0;
+  if (dx == nullptr) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(hash_bwd_dense_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           kDenseMaxBytes);
+      NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      attr_set = true;
+    }
+    while (level0 < grid->num_levels) {
+      const int64_t r1 = static_cast<int64_t>(grid->scalings[level0]) + 1;
+      const int64_t bytes = r1 * r1 * r1 * F * 4;
+      if (bytes > kDenseMaxBytes || M < 65536) break;
+      // enough CTAs to fill the machine at this level's shared-memory footprint, whole rays per chunk
+      const int per_sm = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(4, (220 * 1024) / bytes)));
+      int64_t ctas = static_cast<int64_t>(sm_count()) * per_sm;
+      int64_t chunk = (M + ctas - 1) / ctas;
+      chunk = (chunk + group - 1) / group * group;
+      ctas = (M + chunk - 1) / chunk;
+      hash_bwd_dense_kernel<F><<<static_cast<unsigned>(ctas), kDenseThreads, static_cast<size_t>(bytes), s>>>(
+          g, level0, x, std, dy, dtable, M, group, chunk);
+      count_launch();
+      ++level0;
+    }
+  }
+  if (level0 < grid->num_levels) {
+    const int64_t total = M * (grid->num_levels - level0);
+    const unsigned blocks = blocks_for(total, 256);
+    if (dx != nullptr) {
+      hash_bwd_kernel<F, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total, level0);
+    } else {
+      hash_bwd_kernel<F, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total, level0);
+    }
+  }
+  return finish_launch("nrb_hash_bwd");
+}
+
 extern "C" int nrb_hash_bwd(const nrb_grid_t* grid, const float* x, const float* std, const float* dy, float* dtable,
-                            float* dx, int64_t M, nrb_stream_t stream) {
+                            float* dx, int64_t M, int32_t samples_per_ray, nrb_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   NRB_REQUIRE(x && dy && dtable && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_bwd: null pointer or negative M");
   NRB_REQUIRE(aligned16(dy) && aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_hash_bwd: dy/dtable must be 16-byte aligned");
   if (M == 0) return NRB_OK;
-  const int64_t total = M * grid->num_levels;
   const GridDev g = to_dev(grid);
   auto s = static_cast<cudaStream_t>(stream);
-  const unsigned blocks = blocks_for(total, 256);
+  const int group = (samples_per_ray > 0 && M % samples_per_ray == 0) ? samples_per_ray : 1;
   if (dx != nullptr) {
     cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * M, s);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: memset failed: %s", cudaGetErrorString(e));
-    switch (grid->features_per_level) {
-      case 1: hash_bwd_kernel<1, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-      case 2: hash_bwd_kernel<2, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-      default: hash_bwd_kernel<4, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-    }
-  } else {
-    switch (grid->features_per_level) {
-      case 1: hash_bwd_kernel<1, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-      case 2: hash_bwd_kernel<2, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-      default: hash_bwd_kernel<4, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total); break;
-    }
   }
-  return finish_launch("nrb_hash_bwd");
+  switch (grid->features_per_level) {
+    case 1: return launch_hash_bwd<1>(grid, g, x, std, dy, dtable, dx, M, group, s);
+    case 2: return launch_hash_bwd<2>(grid, g, x, std, dy, dtable, dx, M, group, s);
+    default: return launch_hash_bwd<4>(grid, g, x, std, dy, dtable, dx, M, group, s);
+  }
 }
 
 extern "C" int nrb_frustum_gaussians(const nrb_rays_t* rays, const nrb_intervals_t* iv, float scale, float* x,

@@ -135,7 +135,9 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
           const float v = __shfl_down_sync(kFull, incl, o);
           if (lane + o < 32) incl += v;
         }
-        const float later = suffix + (incl - gw);
+        float excl = __shfl_down_sync(kFull, incl, 1);
+      if (lane == 31) excl = 0.0f;
+      const float later = suffix + excl;
         gdens[c] = ok ? (gwt * trans[c] * e - later) * delta[c] : 0.0f;
         if (ok && ddensity != nullptr) gdens[c] += ddensity[n * S + i];
         suffix += __shfl_sync(kFull, incl, 0);

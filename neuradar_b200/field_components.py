@@ -287,4 +287,4 @@ class NeuRADHashEncoding(nn.Module):
     def encode_samples(self, rays: F.RayData, iv: F.SampleIntervals) -> Tensor:
         """Fast path from per-ray data: gaussians + contraction in one kernel, then the weighted hash encode."""
         x, std = F.frustum_gaussians(rays, iv, self.static_scale)
-        return F.hash_encode(x, self.static_grid.hash_table, self.static_grid.spec, std)
+        return F.hash_encode(x, self.static_grid.hash_table, self.static_grid.spec, std, samples_per_ray=iv.num_samples)

@@ -135,7 +135,7 @@ def _lib_():
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, table, std, spec: GridSpec):
+    def forward(ctx, x, table, std, spec: GridSpec, samples_per_ray: int = 0):
         x = f32c(x)
         table = f32c(table)
         std = None if std is None else f32c(std.reshape(-1))
@@ -145,6 +145,7 @@ class _HashEncode(torch.autograd.Function):
         _lib.call("nrb_hash_fwd", C.byref(g), ptr(x), ptr(std), ptr(out), M, stream_ptr(), tag="nrb_hash_fwd:" + spec.tag)
         ctx.save_for_backward(x, table, std)
         ctx.spec = spec
+        ctx.samples_per_ray = int(samples_per_ray)
         return out
 
     @staticmethod
@@ -157,14 +158,15 @@ class _HashEncode(torch.autograd.Function):
         dtable = torch.zeros_like(table)
         dx = torch.empty_like(x) if need_dx else None
         g = spec.struct(table)
-        _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], stream_ptr(),
-                  tag="nrb_hash_bwd:" + spec.tag)
-        return dx, dtable, None, None
+        _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], ctx.samples_per_ray,
+                  stream_ptr(), tag="nrb_hash_bwd:" + spec.tag)
+        return dx, dtable, None, None, None
 
 
-def hash_encode(x: Tensor, table: Tensor, spec: GridSpec, std: Optional[Tensor] = None) -> Tensor:
-    """HashEncoding.forward on points x [M,3]; with `std` [M] also applies the per-level anti-alias weights."""
-    return _HashEncode.apply(x, table, std, spec)
+def hash_encode(x: Tensor, table: Tensor, spec: GridSpec, std: Optional[Tensor] = None, samples_per_ray: int = 0) -> Tensor:
+    """HashEncoding.forward on points x [M,3]; with `std` [M] also applies the per-level anti-alias weights.
+    `samples_per_ray` is a layout hint for the backward kernel (runs of consecutive samples of one ray)."""
+    return _HashEncode.apply(x, table, std, spec, samples_per_ray)
 
 
 def hash_indices(x: Tensor, spec: GridSpec) -> Tensor:
