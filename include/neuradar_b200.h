@@ -103,10 +103,12 @@ int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float* std, float
 int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t* idx, int64_t M, nrb_stream_t stream);
 /* Backward of nrb_hash_fwd: dtable [L*T, F] += scatter(dy [M, L*F]);  dx [M,3] (optional, may be NULL) is
  * OVERWRITTEN with the gradient through the in-cell offsets (floor/ceil have zero gradient).
- * samples_per_ray (0 = unknown) tells the kernel that x holds runs of that many consecutive samples of one ray, which
- * lets it walk the points ray-fastest where it accumulates in shared memory; it never changes the result. */
+ * `workspace` (optional, 16-byte aligned, nrb_hash_bwd_workspace_bytes(grid, M) bytes, contents ignored) lets the
+ * kernel spread the reductions of the coarse levels over replicated lattices; without it the result is the same,
+ * only slower. */
+int64_t nrb_hash_bwd_workspace_bytes(const nrb_grid_t* grid, int64_t M);
 int nrb_hash_bwd(const nrb_grid_t* grid, const float* x, const float* std, const float* dy, float* dtable, float* dx,
-                 int64_t M, int32_t samples_per_ray, nrb_stream_t stream);
+                 int64_t M, void* workspace, int64_t workspace_bytes, nrb_stream_t stream);
 
 /* ---- sample gaussians + contraction: Frustums.get_fast_isotropic_gaussian(1) (cameras/rays.py:109-124) followed by
  * ScaledSceneContraction(order=inf, scale) on GaussiansStd (field_components/spatial_distortions.py:103-113,132-136).

@@ -84,7 +84,8 @@ SIGNATURES = {
     "nrb_launch_count": [],
     "nrb_hash_fwd": [C.POINTER(Grid), _P, _P, _P, _I64, _P],
     "nrb_hash_indices": [C.POINTER(Grid), _P, _P, _I64, _P],
-    "nrb_hash_bwd": [C.POINTER(Grid), _P, _P, _P, _P, _P, _I64, _I32, _P],
+    "nrb_hash_bwd_workspace_bytes": [C.POINTER(Grid), _I64],
+    "nrb_hash_bwd": [C.POINTER(Grid), _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
     "nrb_frustum_gaussians": [C.POINTER(Rays), C.POINTER(Intervals), _F, _P, _P, _P],
     "nrb_mlp_fwd": [C.POINTER(Mlp), _P, _P, _P, _I64, _P],
     "nrb_mlp_bwd": [C.POINTER(Mlp), _P, _P, _P, _P, C.POINTER(MlpGrad), _I64, _P],
@@ -100,7 +101,7 @@ SIGNATURES = {
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
     "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P],
 }
-_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64}
+_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

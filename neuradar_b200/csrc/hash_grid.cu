@@ -83,23 +83,36 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ base, uint32_t r
   }
 }
 
-// Levels [level0, L) with plain vector reductions into the table (levels below level0 are handled by the
-// shared-memory privatised kernel further down).
+// Backward scatter.  Same-row float reductions serialise in L2: 25 M reductions take 0.16 ms when they spread over
+// the 2^19 rows of a res-1024 level and 7 ms when they pile onto the 4913 rows of a res-16 level (measured, B200).
+// Coarse levels are therefore accumulated into `copies[l]` replicas of the level's dense vertex lattice
+// ((res+1)^3 x F floats, a few MB in total, L2 resident); warps are dealt round-robin over the replicas, which
+// divides the per-address contention by the replica count, and a small fold kernel adds the replicas into the
+// hashed rows.  Replica counts are chosen so that every level sees about the same number of reductions per address
+// as the finest one.  Shared-memory privatisation was measured and rejected: fp32 shared atomics are CAS loops
+// (ATOMS.CAST.SPIN) on sm_100 and cost ~1 ms per level.
+struct BwdPlan {
+  float* scratch;                   // replicated lattices, zeroed by the launcher
+  int64_t offset[NRB_MAX_LEVELS];   // float offset of level l's first replica
+  int copies[NRB_MAX_LEVELS];       // 0/1: scatter straight into the table
+  int r1[NRB_MAX_LEVELS];           // res + 1
+};
+
 template <int F, bool kNeedDx>
-__global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
-                                                       const float* __restrict__ std, const float* __restrict__ dy,
-                                                       float* __restrict__ dtable, float* __restrict__ dx,
-                                                       int64_t total, int level0) {
+__global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ GridDev g,
+                                                       const __grid_constant__ BwdPlan plan,
+                                                       const float* __restrict__ x, const float* __restrict__ std,
+                                                       const float* __restrict__ dy, float* __restrict__ dtable,
+                                                       float* __restrict__ dx, int64_t total) {
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (gid >= total) return;
-  const int nl = g.num_levels - level0;
-  const int64_t m = gid / nl;
-  const int l = level0 + static_cast<int>(gid - m * nl);
+  const int64_t m = gid / g.num_levels;
+  const int l = static_cast<int>(gid - m * g.num_levels);
   const float scal = g.scalings[l];
-  const Cell c = locate_cell(__ldg(x + 3 * m), __ldg(x + 3 * m + 1), __ldg(x + 3 * m + 2), scal,
-                             (1u << g.log2_size) - 1u);
+  const float px = __ldg(x + 3 * m), py = __ldg(x + 3 * m + 1), pz = __ldg(x + 3 * m + 2);
+  const Cell c = locate_cell(px, py, pz, scal, (1u << g.log2_size) - 1u);
   using V = typename Feat<F>::type;
-  const V gv = __ldg(reinterpret_cast<const V*>(dy) + m * g.num_levels + l);
+  const V gv = __ldg(reinterpret_cast<const V*>(dy) + gid);
   float gr[F];
   if constexpr (F == 1) {
     gr[0] = gv;
@@ -141,99 +154,63 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ G
   }
   float w[8];
   corner_weights(c, w);
+  const int copies = plan.copies[l];
+  if (copies > 1) {
+    const int R1 = plan.r1[l];
+    const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
+    const int xf = static_cast<int>(floorf(sx)), yf = static_cast<int>(floorf(sy)), zf = static_cast<int>(floorf(sz));
+    const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
+    if (xf >= 0 && yf >= 0 && zf >= 0 && xc < R1 && yc < R1 && zc < R1) {
+      const unsigned warp_global = static_cast<unsigned>(gid >> 5);
+      float* rep = plan.scratch + plan.offset[l] +
+                   static_cast<size_t>(warp_global % static_cast<unsigned>(copies)) * (static_cast<size_t>(R1) * R1 * R1 * F);
+      const int cx[8] = {xc, xc, xf, xf, xc, xc, xf, xf};
+      const int cy[8] = {yc, yf, yf, yc, yc, yf, yf, yc};
+      const int cz[8] = {zc, zc, zc, zc, zf, zf, zf, zf};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) scatter_row<F>(rep, static_cast<uint32_t>((cz[k] * R1 + cy[k]) * R1 + cx[k]), gr, w[k]);
+      return;
+    }
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) scatter_row<F>(dtable + level_off, c.row[k], gr, w[k]);
 }
 
-// Coarse levels: a level whose dense vertex lattice (res+1)^3 x F floats fits in shared memory is accumulated there
-// first.  Millions of samples fall on a few thousand table rows at these levels, and same-row float reductions
-// serialise in L2 (measured: 25 M reductions on the 4913 rows of a res-16 level take 7 ms, on a res-1024 level
-// 0.16 ms).  Each CTA privatises the lattice, consumes a contiguous chunk of samples (walked ray-fastest so that the
-// lanes of a warp sit in different cells) and flushes each touched vertex with ONE reduction to its hashed row.
-constexpr int kDenseThreads = 512;
-constexpr int kDenseMaxBytes = 200 * 1024;
-
+// Adds the replicas of every replicated level into the table: one thread per lattice vertex.
 template <int F>
-__global__ void __launch_bounds__(kDenseThreads) hash_bwd_dense_kernel(
-    const __grid_constant__ GridDev g, int level, const float* __restrict__ x, const float* __restrict__ std,
-    const float* __restrict__ dy, float* __restrict__ dtable, int64_t M, int group, int64_t chunk) {
-  extern __shared__ __align__(16) float acc[];
-  const float scal = g.scalings[level];
-  const int R1 = static_cast<int>(scal) + 1;
-  const int V = R1 * R1 * R1;
-  for (int i = threadIdx.x; i < V * F; i += kDenseThreads) acc[i] = 0.0f;
-  __syncthreads();
-  const uint32_t mask = (1u << g.log2_size) - 1u;
-  float* level_base = dtable + (static_cast<size_t>(level) << g.log2_size) * F;
-  const int64_t m0 = static_cast<int64_t>(blockIdx.x) * chunk;
-  const int count = static_cast<int>(min(chunk, M - m0));
-  const int nr = (count % group == 0) ? count / group : count;  // rays in this chunk (whole rays when possible)
-  const int ns = (count % group == 0) ? group : 1;
-  for (int idx = threadIdx.x; idx < count; idx += kDenseThreads) {
-    const int s = idx / nr, r = idx - s * nr;
-    const int64_t m = m0 + static_cast<int64_t>(r) * ns + s;
-    const float px = __ldg(x + 3 * m), py = __ldg(x + 3 * m + 1), pz = __ldg(x + 3 * m + 2);
-    using Vt = typename Feat<F>::type;
-    const Vt gv = __ldg(reinterpret_cast<const Vt*>(dy) + m * g.num_levels + level);
-    float gr[F];
-    if constexpr (F == 1) {
-      gr[0] = gv;
-    } else if constexpr (F == 2) {
-      gr[0] = gv.x;
-      gr[1] = gv.y;
-    } else {
-      gr[0] = gv.x;
-      gr[1] = gv.y;
-      gr[2] = gv.z;
-      gr[3] = gv.w;
-    }
-    if (std != nullptr) {
-      const float lw = level_weight(scal, __ldg(std + m));
-#pragma unroll
-      for (int j = 0; j < F; ++j) gr[j] *= lw;
-    }
-    const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
-    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
-    const int xf = static_cast<int>(fx), yf = static_cast<int>(fy), zf = static_cast<int>(fz);
-    const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
-    Cell c;
-    c.ox = sub(sx, fx);
-    c.oy = sub(sy, fy);
-    c.oz = sub(sz, fz);
-    float w[8];
-    corner_weights(c, w);
-    const bool inside = xf >= 0 && yf >= 0 && zf >= 0 && xc < R1 && yc < R1 && zc < R1;
-    const int cx[8] = {xc, xc, xf, xf, xc, xc, xf, xf};
-    const int cy[8] = {yc, yf, yf, yc, yc, yf, yf, yc};
-    const int cz[8] = {zc, zc, zc, zc, zf, zf, zf, zf};
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      if (inside) {
-        float* p = acc + ((cz[k] * R1 + cy[k]) * R1 + cx[k]) * F;
-#pragma unroll
-        for (int j = 0; j < F; ++j) atomicAdd(p + j, gr[j] * w[k]);
-      } else {  // points outside the unit cube: straight to the hashed row
-        const uint32_t row = (static_cast<uint32_t>(cx[k]) ^ (static_cast<uint32_t>(cy[k]) * kPrimeY) ^
-                              (static_cast<uint32_t>(cz[k]) * kPrimeZ)) & mask;
-        scatter_row<F>(level_base, row, gr, w[k]);
-      }
-    }
+__global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constant__ GridDev g,
+                                                            const __grid_constant__ BwdPlan plan,
+                                                            float* __restrict__ dtable, int64_t total_vertices) {
+  int64_t v = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (v >= total_vertices) return;
+  int l = 0;
+  for (; l < g.num_levels; ++l) {
+    if (plan.copies[l] <= 1) continue;
+    const int64_t nv = static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l];
+    if (v < nv) break;
+    v -= nv;
   }
-  __syncthreads();
-  for (int v = threadIdx.x; v < V; v += kDenseThreads) {
-    float val[F];
-    bool any = false;
+  if (l >= g.num_levels) return;
+  const int R1 = plan.r1[l];
+  const int64_t nv = static_cast<int64_t>(R1) * R1 * R1;
+  const float* rep = plan.scratch + plan.offset[l] + v * F;
+  float sum[F];
 #pragma unroll
-    for (int j = 0; j < F; ++j) {
-      val[j] = acc[v * F + j];
-      any |= (val[j] != 0.0f);
-    }
-    if (!any) continue;
-    const int ix = v % R1, iy = (v / R1) % R1, iz = v / (R1 * R1);
-    const uint32_t row = (static_cast<uint32_t>(ix) ^ (static_cast<uint32_t>(iy) * kPrimeY) ^
-                          (static_cast<uint32_t>(iz) * kPrimeZ)) & mask;
-    scatter_row<F>(level_base, row, val, 1.0f);
+  for (int j = 0; j < F; ++j) sum[j] = 0.0f;
+  for (int cpy = 0; cpy < plan.copies[l]; ++cpy) {
+    float t[F];
+    load_row<F>(rep + static_cast<size_t>(cpy) * nv * F, 0, t);
+#pragma unroll
+    for (int j = 0; j < F; ++j) sum[j] += t[j];
   }
+  bool any = false;
+#pragma unroll
+  for (int j = 0; j < F; ++j) any |= (sum[j] != 0.0f);
+  if (!any) return;
+  const int ix = static_cast<int>(v % R1), iy = static_cast<int>((v / R1) % R1), iz = static_cast<int>(v / (R1 * R1));
+  const uint32_t row = (static_cast<uint32_t>(ix) ^ (static_cast<uint32_t>(iy) * kPrimeY) ^
+                        (static_cast<uint32_t>(iz) * kPrimeZ)) & ((1u << g.log2_size) - 1u);
+  scatter_row<F>(dtable + (static_cast<size_t>(l) << g.log2_size) * F, row, sum, 1.0f);
 }
 
 __global__ void __launch_bounds__(256) frustum_gaussians_kernel(const float* __restrict__ origins,
@@ -289,64 +266,86 @@ extern "C" int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t*
   return finish_launch("nrb_hash_indices");
 }
 
+// Replica plan: as many copies of a coarse level's lattice as it takes to bring its reductions per address down to
+// those of a level that fills the whole table, within the caller's workspace.
+static int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
+  const int F = grid->features_per_level;
+  const double table_rows = static_cast<double>(int64_t{1} << grid->log2_hashmap_size);
+  int64_t floats = 0;
+  for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
+    plan->copies[l] = 0;
+    plan->offset[l] = 0;
+    plan->r1[l] = 0;
+    if (l >= grid->num_levels || M < (int64_t{1} << 16)) continue;
+    const int64_t r1 = static_cast<int64_t>(grid->scalings[l]) + 1;
+    const double verts = static_cast<double>(r1) * r1 * r1;
+    if (verts * 1.5 > table_rows || r1 > 1024) continue;  // the level already spreads over (most of) the table
+    int copies = static_cast<int>(table_rows / verts + 0.5);
+    copies = std::min(copies, 128);
+    while (copies > 1 && static_cast<double>(copies) * verts * F * 4 > 8.0 * 1024 * 1024) --copies;
+    if (copies <= 1) continue;
+    plan->copies[l] = copies;
+    plan->r1[l] = static_cast<int>(r1);
+    plan->offset[l] = floats;
+    floats += static_cast<int64_t>(copies) * r1 * r1 * r1 * F;
+    floats = (floats + 3) & ~int64_t{3};
+  }
+  return floats * 4;
+}
+
+extern "C" int64_t nrb_hash_bwd_workspace_bytes(const nrb_grid_t* grid, int64_t M) {
+  if (grid == nullptr || check_grid(grid) != NRB_OK) return -1;
+  BwdPlan plan;
+  return plan_hash_bwd(grid, M, &plan);
+}
+
 template <int F>
 static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float* x, const float* std, const float* dy,
-                           float* dtable, float* dx, int64_t M, int group, cudaStream_t s) {
-  // dense-privatised coarse levels (not used when the input gradient is requested: that path needs the features)
-  int level0 = 0;
-  if (dx == nullptr) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(hash_bwd_dense_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kDenseMaxBytes);
-      NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-      attr_set = true;
-    }
-    while (level0 < grid->num_levels) {
-      const int64_t r1 = static_cast<int64_t>(grid->scalings[level0]) + 1;
-      const int64_t bytes = r1 * r1 * r1 * F * 4;
-      if (bytes > kDenseMaxBytes || M < 65536) break;
-      // enough CTAs to fill the machine at this level's shared-memory footprint, whole rays per chunk
-      const int per_sm = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(4, (220 * 1024) / bytes)));
-      int64_t ctas = static_cast<int64_t>(sm_count()) * per_sm;
-      int64_t chunk = (M + ctas - 1) / ctas;
-      chunk = (chunk + group - 1) / group * group;
-      ctas = (M + chunk - 1) / chunk;
-      hash_bwd_dense_kernel<F><<<static_cast<unsigned>(ctas), kDenseThreads, static_cast<size_t>(bytes), s>>>(
-          g, level0, x, std, dy, dtable, M, group, chunk);
-      count_launch();
-      ++level0;
-    }
+                           float* dtable, float* dx, int64_t M, void* workspace, int64_t workspace_bytes,
+                           cudaStream_t s) {
+  BwdPlan plan;
+  const int64_t need = plan_hash_bwd(grid, M, &plan);
+  int64_t vertices = 0;
+  if (need > 0 && workspace != nullptr && workspace_bytes >= need && aligned16(workspace)) {
+    plan.scratch = static_cast<float*>(workspace);
+    cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(need), s);
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: memset failed: %s", cudaGetErrorString(e));
+    for (int l = 0; l < grid->num_levels; ++l)
+      if (plan.copies[l] > 1) vertices += static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l];
+  } else {  // no (or too small a) workspace: every level scatters straight into the table
+    plan.scratch = nullptr;
+    for (int l = 0; l < NRB_MAX_LEVELS; ++l) plan.copies[l] = 0;
   }
-  if (level0 < grid->num_levels) {
-    const int64_t total = M * (grid->num_levels - level0);
-    const unsigned blocks = blocks_for(total, 256);
-    if (dx != nullptr) {
-      hash_bwd_kernel<F, true><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total, level0);
-    } else {
-      hash_bwd_kernel<F, false><<<blocks, 256, 0, s>>>(g, x, std, dy, dtable, dx, total, level0);
-    }
+  const int64_t total = M * grid->num_levels;
+  const unsigned blocks = blocks_for(total, 256);
+  if (dx != nullptr) {
+    hash_bwd_kernel<F, true><<<blocks, 256, 0, s>>>(g, plan, x, std, dy, dtable, dx, total);
+  } else {
+    hash_bwd_kernel<F, false><<<blocks, 256, 0, s>>>(g, plan, x, std, dy, dtable, dx, total);
+  }
+  if (vertices > 0) {
+    count_launch();
+    hash_bwd_fold_kernel<F><<<blocks_for(vertices, 256), 256, 0, s>>>(g, plan, dtable, vertices);
   }
   return finish_launch("nrb_hash_bwd");
 }
 
 extern "C" int nrb_hash_bwd(const nrb_grid_t* grid, const float* x, const float* std, const float* dy, float* dtable,
-                            float* dx, int64_t M, int32_t samples_per_ray, nrb_stream_t stream) {
+                            float* dx, int64_t M, void* workspace, int64_t workspace_bytes, nrb_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   NRB_REQUIRE(x && dy && dtable && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_bwd: null pointer or negative M");
   NRB_REQUIRE(aligned16(dy) && aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_hash_bwd: dy/dtable must be 16-byte aligned");
   if (M == 0) return NRB_OK;
   const GridDev g = to_dev(grid);
   auto s = static_cast<cudaStream_t>(stream);
-  const int group = (samples_per_ray > 0 && M % samples_per_ray == 0) ? samples_per_ray : 1;
   if (dx != nullptr) {
     cudaError_t e = cudaMemsetAsync(dx, 0, sizeof(float) * 3 * M, s);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: memset failed: %s", cudaGetErrorString(e));
   }
   switch (grid->features_per_level) {
-    case 1: return launch_hash_bwd<1>(grid, g, x, std, dy, dtable, dx, M, group, s);
-    case 2: return launch_hash_bwd<2>(grid, g, x, std, dy, dtable, dx, M, group, s);
-    default: return launch_hash_bwd<4>(grid, g, x, std, dy, dtable, dx, M, group, s);
+    case 1: return launch_hash_bwd<1>(grid, g, x, std, dy, dtable, dx, M, workspace, workspace_bytes, s);
+    case 2: return launch_hash_bwd<2>(grid, g, x, std, dy, dtable, dx, M, workspace, workspace_bytes, s);
+    default: return launch_hash_bwd<4>(grid, g, x, std, dy, dtable, dx, M, workspace, workspace_bytes, s);
   }
 }
 

@@ -129,6 +129,21 @@ def _lib_():
     return _lib.load()
 
 
+_WORKSPACES = {}
+
+
+def _workspace(nbytes: int, device):
+    """Scratch memory for kernels that want it (grown on demand, one buffer per device, reused across calls on the
+    same stream order)."""
+    if nbytes <= 0:
+        return None, 0
+    buf = _WORKSPACES.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((nbytes,), device=device, dtype=torch.uint8)
+        _WORKSPACES[device] = buf
+    return buf.data_ptr(), nbytes
+
+
 # ------------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------------
@@ -158,7 +173,8 @@ class _HashEncode(torch.autograd.Function):
         dtable = torch.zeros_like(table)
         dx = torch.empty_like(x) if need_dx else None
         g = spec.struct(table)
-        _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], ctx.samples_per_ray,
+        ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), x.shape[0])), x.device)
+        _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], ws, ws_bytes,
                   stream_ptr(), tag="nrb_hash_bwd:" + spec.tag)
         return dx, dtable, None, None, None
 

@@ -216,7 +216,11 @@ def test_samplers_golden(nb, golden, mode):
     assert float((inds.cpu() != ref_inds).float().mean()) <= 1e-3
     # bins in low-density intervals amplify the 1-ulp cdf difference by 1/pdf (<= 1/histogram_padding)
     assert float((sb1.cpu() - g[f"{mode}_sbins1"]).abs().max()) <= 5e-6
-    assert rel_err(eb1, g[f"{mode}_ebins1"]) <= 1e-5
+    # stage level: the kernel's euclidean bins are the reference's spacing_to_euclidean_fn of the kernel's own bins
+    sp = O.Spacing(O.power_fn(g["nears"] * 0.1, -1.0), O.power_fn(g["fars"] * 0.1, -1.0), -1.0, 0.1)
+    assert torch.equal(eb1.cpu(), sp.to_euclidean(sb1.cpu()))
+    # end to end the inverse power transform amplifies bin differences by up to ~1e7 m per unit of s at the far end
+    assert rel_err(eb1, g[f"{mode}_ebins1"]) <= 1e-3
     assert bool((sb1[:, 1:] >= sb1[:, :-1]).all()), "sampled bins must be sorted"
 
 
@@ -461,7 +465,7 @@ def test_full_size_properties(nb):
         assert float(w.min()) >= 0.0 and float(w.sum(dim=1).max()) <= 1.0 + 1e-4
     for rs in out["ray_samples_list"][:2]:
         eb = rs.euclidean_bins
-        assert bool((eb[:, 1:] >= eb[:, :-1]).all()) and float(eb.min()) >= 0.0 and float(eb.max()) <= 20000.0 * (1 + 1e-5)
+        assert bool((eb[:, 1:] >= eb[:, :-1]).all()) and float(eb.min()) >= 0.0 and float(eb.max()) <= 20000.0 * (1 + 1e-3)  # the inverse power transform amplifies 1 ulp of s by ~1e3 at the far end
     nb.bench_loss(out).backward()
     for name, p in model.named_parameters():
         if name.startswith("proposal_fields.0"):
