@@ -123,6 +123,33 @@ int nrb_mlp_fwd(const nrb_mlp_t* mlp, const float* x, float* y, float* hidden, i
 int nrb_mlp_bwd(const nrb_mlp_t* mlp, const float* x, const float* hidden, const float* dy, float* dx,
                 const nrb_mlp_grad_t* grads, int64_t M, nrb_stream_t stream);
 
+/* ---- fused NeuRAD field MLP on tcgen05 tensor cores: everything NeuRADField.forward does after the hash grid
+ * (fields/neurad_field.py:132-152; replaces the two tcnn FullyFusedMLP networks, mlp.py:109-127):
+ *   geo = mlp_geo(x) [32 -> 32 ReLU -> 33]; sdf, emb = split(geo, [1, 32]);
+ *   feature = emb + mlp_feature([emb, sh]) [48 -> 32 ReLU -> 32 ReLU -> 32]; alpha = sigmoid(-sdf (|beta| + beta_min)).
+ * weights[0..1] = mlp_geo.layers.{0,1}.weight, weights[2..4] = mlp_feature.layers.{0,1,2}.weight ([out,in] row-major),
+ * biases likewise (may be NULL); x [M,32] hash features; sh [N_rays,16] SH basis of each ray's direction, row m of x
+ * belongs to ray m / samples_per_ray.  fp32 in and out; products are evaluated as 3xTF32 with fp32 accumulation. */
+typedef struct {
+  const float* weights[5];
+  const float* biases[5];
+  const float* beta;
+  float beta_min;
+} nrb_field_mlp_t;
+/* Activations the backward pass needs, each [M,32] row-major; pass NULL (or NULL members) for inference. */
+typedef struct {
+  float* h1;
+  float* emb;
+  float* g1;
+  float* g2;
+} nrb_field_saved_t;
+int nrb_field_mlp_fwd(const nrb_field_mlp_t* mlp, const float* x, const float* sh, int32_t samples_per_ray, int64_t M,
+                      float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved, nrb_stream_t stream);
+/* One linear layer y = x W^T + b (optional ReLU) through the same tcgen05 building blocks (K = 32 or 48,
+ * n_out <= 48): the unit test of the descriptor / layout conventions. */
+int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,
+                  float* y, nrb_stream_t stream);
+
 /* ---- degree-4 real spherical harmonics of (d+1)/2: SHEncoding.pytorch_fwd on get_normalized_directions
  * (encodings.py:797-805, utils/math.py:31-94, fields/base_field.py:136-142).  dirs [M,3] -> out [M,16]. */
 int nrb_sh16(const float* dirs, float* out, int64_t M, int32_t normalize_to_unit_cube, nrb_stream_t stream);

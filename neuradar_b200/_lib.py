@@ -68,6 +68,19 @@ class MlpGrad(C.Structure):
     ]
 
 
+class FieldMlp(C.Structure):
+    _fields_ = [
+        ("weights", C.c_void_p * 5),
+        ("biases", C.c_void_p * 5),
+        ("beta", C.c_void_p),
+        ("beta_min", C.c_float),
+    ]
+
+
+class FieldSaved(C.Structure):
+    _fields_ = [("h1", C.c_void_p), ("emb", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p)]
+
+
 class Spacing(C.Structure):
     _fields_ = [("lam", C.c_float), ("scaling", C.c_float)]
 
@@ -90,6 +103,8 @@ SIGNATURES = {
     "nrb_mlp_fwd": [C.POINTER(Mlp), _P, _P, _P, _I64, _P],
     "nrb_mlp_bwd": [C.POINTER(Mlp), _P, _P, _P, _P, C.POINTER(MlpGrad), _I64, _P],
     "nrb_sh16": [_P, _P, _I64, _I32, _P],
+    "nrb_field_mlp_fwd": [C.POINTER(FieldMlp), _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(FieldSaved), _P],
+    "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
     "nrb_pdf_sample": [C.POINTER(Rays), Spacing, _P, _P, _I32, _P, _P, _I32, _F, _F, _P, _P, _P, _P, _P],
     "nrb_density_weights_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],

@@ -1,0 +1,190 @@
+// tcgen05 / TMEM building blocks for the fused NeuRAD field MLP (sm_100a).
+//
+// Operand layout.  Every operand tile lives in shared memory in the canonical no-swizzle ("interleave") UMMA
+// layout: 8-row x 16-byte core matrices (8 rows x 4 tf32 values, 128 contiguous bytes).  For a tile of R rows and
+// K columns:   byte_offset(r, k) = (r / 8) * (K / 4) * 128 + (k / 4) * 128 + (r % 8) * 16 + (k % 4) * 4.
+//   * As a K-major operand (reduction over the columns): LBO = 128 (next 4 columns), SBO = (K/4)*128 (next 8 rows).
+//   * The same bytes are a valid MN-major operand with the roles of rows and columns swapped (reduction over the
+//     ROWS): LBO = (K/4)*128, SBO = 128.  The backward pass uses this to form X^T dY and dY W without re-staging.
+// One thread owns one row, so a row is written as K/4 16-byte stores; the 8 lanes of a quarter warp cover 128
+// contiguous bytes, i.e. the stores are bank-conflict free.
+//
+// Precision.  The reference MLPs run in fp32 and parity is 1e-3 relative on outputs AND gradients, through five
+// chained layers and a sigmoid with slope 20.  kind::tf32 keeps 10 mantissa bits, so every operand is split into
+// hi = top 11 significant bits and lo = x - hi (exact), and each product is issued as hi*hi + hi*lo + lo*hi with
+// fp32 accumulation in TMEM ("3xTF32"), which is accurate to ~2^-20.  The tensor pipe has two orders of magnitude of
+// headroom for this workload, so the 3x MMA count is free.
+#pragma once
+
+#include "common.cuh"
+
+namespace nrb {
+namespace tc {
+
+constexpr int kRows = 128;  // rows (samples) per tile = UMMA M = TMEM lanes
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// 64-bit shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 (SWIZZLE_NONE) [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+// 32-bit instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, M = 128.
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+  const uint32_t addr = smem_u32(mbar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {  // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+
+template <int kCols>
+__device__ __forceinline__ void tmem_free(uint32_t taddr) {  // the allocating warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+
+// TMEM -> registers: lane i of warp w receives row 32*(w%4)+i, 16 consecutive fp32 columns starting at `taddr`.
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Read kN (multiple of 16) accumulator columns of this thread's row.
+template <int kN>
+__device__ __forceinline__ void tmem_load_row(uint32_t tmem_base, int warp, int col0, float (&v)[kN]) {
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(col0);
+#pragma unroll
+  for (int c = 0; c < kN / 16; ++c) {
+    float t[16];
+    tmem_ld16(taddr + c * 16, t);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[c * 16 + i] = t[i];
+  }
+  tmem_ld_wait();
+}
+
+// byte offset of (row, 4-column chunk) in a canonical tile with K columns
+__device__ __forceinline__ uint32_t tile_offset(int row, int chunk, int K) {
+  return static_cast<uint32_t>((row >> 3) * (K / 4) * 128 + chunk * 128 + (row & 7) * 16);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Write one row (K values, K % 4 == 0) of an operand tile as its hi / lo tf32 halves.
+template <int K>
+__device__ __forceinline__ void store_row_split(char* hi_tile, char* lo_tile, int row, const float (&v)[K]) {
+#pragma unroll
+  for (int c = 0; c < K / 4; ++c) {
+    float4 h, l;
+    h.x = tf32_hi(v[4 * c + 0]);
+    h.y = tf32_hi(v[4 * c + 1]);
+    h.z = tf32_hi(v[4 * c + 2]);
+    h.w = tf32_hi(v[4 * c + 3]);
+    l.x = v[4 * c + 0] - h.x;
+    l.y = v[4 * c + 1] - h.y;
+    l.z = v[4 * c + 2] - h.z;
+    l.w = v[4 * c + 3] - h.w;
+    const uint32_t off = tile_offset(row, c, K);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+  }
+}
+
+// Stage a row-major weight matrix w[n_rows][K] (global) as a canonical tile padded to n_pad rows, hi and lo halves.
+// Called by the whole CTA.
+__device__ __forceinline__ void stage_weight_split(const float* __restrict__ w, int n_rows, int n_pad, int K, char* hi_tile,
+                                                   char* lo_tile) {
+  for (int e = threadIdx.x; e < n_pad * K; e += blockDim.x) {
+    const int r = e / K, k = e - r * K;
+    const float v = (r < n_rows) ? __ldg(w + r * K + k) : 0.0f;
+    const float h = tf32_hi(v);
+    const uint32_t off = tile_offset(r, k >> 2, K) + (k & 3) * 4;
+    *reinterpret_cast<float*>(hi_tile + off) = h;
+    *reinterpret_cast<float*>(lo_tile + off) = v - h;
+  }
+}
+
+// D[128, N] (+)= A[128, K] * B[N, K]^T with A and B K-major canonical tiles (hi/lo pairs), 3xTF32.  One thread.
+__device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi,
+                                                  uint32_t b_lo, int K, int N, bool accumulate_first) {
+  const uint32_t idesc = make_idesc(N, 0, 0);
+  const uint32_t sbo = static_cast<uint32_t>(K / 4) * 128u;
+  bool acc = accumulate_first;
+  for (int k = 0; k < K / 8; ++k) {
+    const uint32_t koff = static_cast<uint32_t>(k) * 256u;  // 8 tf32 = two 16-byte chunks = two core matrices
+    const uint64_t ah = make_desc(a_hi + koff, 128, sbo), al = make_desc(a_lo + koff, 128, sbo);
+    const uint64_t bh = make_desc(b_hi + koff, 128, sbo), bl = make_desc(b_lo + koff, 128, sbo);
+    mma_tf32(d_tmem, al, bh, idesc, acc);  // small terms first
+    mma_tf32(d_tmem, ah, bl, idesc, true);
+    mma_tf32(d_tmem, ah, bh, idesc, true);
+    acc = true;
+  }
+}
+
+}  // namespace tc
+}  // namespace nrb

@@ -274,6 +274,49 @@ def mlp_forward(x: Tensor, weights: Sequence[Tensor], biases: Sequence[Optional[
     return _MlpForward.apply(x, len(weights), *weights, *biases)
 
 
+def tc_linear(x: Tensor, weight: Tensor, bias: Optional[Tensor], relu: bool = False) -> Tensor:
+    """y = x W^T + b through the tcgen05 building blocks (K in {32, 48}, out <= 48); forward only, for testing."""
+    x, weight = f32c(x), f32c(weight)
+    bias = None if bias is None else f32c(bias)
+    M, K = x.shape
+    y = torch.empty((M, weight.shape[0]), device=x.device, dtype=torch.float32)
+    _lib.call("nrb_tc_linear", ptr(x), ptr(weight), ptr(bias), K, weight.shape[0], int(relu), M, ptr(y), stream_ptr())
+    return y
+
+
+def _field_struct(weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float):
+    m = _lib.FieldMlp()
+    for i in range(5):
+        m.weights[i] = ptr(weights[i])
+        m.biases[i] = ptr(biases[i])
+    m.beta = ptr(beta)
+    m.beta_min = float(beta_min)
+    return m
+
+
+def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Tensor],
+                      biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float, save: bool = False):
+    """Inference-only entry of the fused tensor-core field MLP: (feature [M,32], sdf [M], alpha [M], saved)."""
+    x, sh = f32c(x), f32c(sh)
+    weights = [f32c(w) for w in weights]
+    biases = [None if b is None else f32c(b) for b in biases]
+    beta = f32c(beta)
+    M = x.shape[0]
+    dev = x.device
+    feature = torch.empty((M, 32), device=dev, dtype=torch.float32)
+    sdf = torch.empty((M,), device=dev, dtype=torch.float32)
+    alpha = torch.empty((M,), device=dev, dtype=torch.float32)
+    saved = None
+    sv = _lib.FieldSaved()
+    if save:
+        saved = [torch.empty((M, 32), device=dev, dtype=torch.float32) for _ in range(4)]
+        sv.h1, sv.emb, sv.g1, sv.g2 = (ptr(t) for t in saved)
+    m = _field_struct(weights, biases, beta, beta_min)
+    _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
+              ptr(alpha), C.byref(sv), stream_ptr())
+    return feature, sdf, alpha, saved
+
+
 def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:
     """16 real SH basis values of directions [M,3]; no gradient (reference: torch.no_grad)."""
     d = f32c(directions.detach())
