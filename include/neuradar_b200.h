@@ -145,6 +145,33 @@ typedef struct {
 } nrb_field_saved_t;
 int nrb_field_mlp_fwd(const nrb_field_mlp_t* mlp, const float* x, const float* sh, int32_t samples_per_ray, int64_t M,
                       float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved, nrb_stream_t stream);
+/* Backward of nrb_field_mlp_fwd.  Inputs: the forward input x, the saved activations, sh, the forward outputs sdf and
+ * alpha, and the upstream gradients dfeature [M,32], dsdf [M] (optional) and dalpha [M] (optional).
+ * Outputs: dx [M,32] (optional, gradient w.r.t. the hash features), and ACCUMULATED parameter gradients: dweights[i]
+ * / dbiases[i] shaped like the parameters (each optional) and dbeta [1] = d loss / d(|beta| + beta_min). */
+typedef struct {
+  const float* x;
+  const float* h1;
+  const float* emb;
+  const float* g1;
+  const float* g2;
+  const float* sh;
+  const float* sdf;
+  const float* alpha;
+  const float* dfeature;
+  const float* dsdf;
+  const float* dalpha;
+} nrb_field_bwd_in_t;
+typedef struct {
+  float* dx;
+  float* dweights[5];
+  float* dbiases[5];
+  float* dbeta;
+} nrb_field_bwd_out_t;
+int nrb_field_mlp_bwd(const nrb_field_mlp_t* mlp, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
+                      int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
+/* Debug: dumps [128 lanes][32 columns] of an M = 64 tcgen05 accumulator whose row j holds the constant j + 1. */
+int nrb_tc_probe_m64(float* dump, nrb_stream_t stream);
 /* One linear layer y = x W^T + b (optional ReLU) through the same tcgen05 building blocks (K = 32 or 48,
  * n_out <= 48): the unit test of the descriptor / layout conventions. */
 int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,

@@ -81,6 +81,14 @@ class FieldSaved(C.Structure):
     _fields_ = [("h1", C.c_void_p), ("emb", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p)]
 
 
+class FieldBwdIn(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("x", "h1", "emb", "g1", "g2", "sh", "sdf", "alpha", "dfeature", "dsdf", "dalpha")]
+
+
+class FieldBwdOut(C.Structure):
+    _fields_ = [("dx", C.c_void_p), ("dweights", C.c_void_p * 5), ("dbiases", C.c_void_p * 5), ("dbeta", C.c_void_p)]
+
+
 class Spacing(C.Structure):
     _fields_ = [("lam", C.c_float), ("scaling", C.c_float)]
 
@@ -105,6 +113,8 @@ SIGNATURES = {
     "nrb_sh16": [_P, _P, _I64, _I32, _P],
     "nrb_field_mlp_fwd": [C.POINTER(FieldMlp), _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(FieldSaved), _P],
     "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],
+    "nrb_field_mlp_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldBwdIn), C.POINTER(FieldBwdOut), _I32, _I64, _P],
+    "nrb_tc_probe_m64": [_P, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
     "nrb_pdf_sample": [C.POINTER(Rays), Spacing, _P, _P, _I32, _P, _P, _I32, _F, _F, _P, _P, _P, _P, _P],
     "nrb_density_weights_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],

@@ -188,3 +188,72 @@ __device__ __forceinline__ void issue_gemm_kmajor(uint32_t d_tmem, uint32_t a_hi
 
 }  // namespace tc
 }  // namespace nrb
+
+namespace nrb {
+namespace tc {
+
+// 32-bit instruction descriptor with explicit M (64 or 128).
+__device__ __forceinline__ uint32_t make_idesc_m(int m, int n, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(a_mn_major) << 15) |
+         (static_cast<uint32_t>(b_mn_major) << 16) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// D[128, N] (+)= A[128, Kred] * W[Kred, N]: A is a K-major canonical tile with `a_cols` columns (reduction over its
+// columns), W is the canonical tile of a row-major [rows >= Kred][N] matrix read as an MN-major B operand (reduction
+// over its ROWS).  This is dIn = dOut * W with W staged exactly as for the forward pass.  3xTF32.  One thread.
+__device__ __forceinline__ void issue_gemm_a_kmajor_b_mnmajor(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_cols,
+                                                              uint32_t w_hi, uint32_t w_lo, int w_cols, int k_red,
+                                                              bool accumulate_first) {
+  const uint32_t idesc = make_idesc_m(128, w_cols, 0, 1);
+  const uint32_t a_sbo = static_cast<uint32_t>(a_cols / 4) * 128u;
+  const uint32_t w_grp = static_cast<uint32_t>(w_cols / 4) * 128u;  // next 8 rows of W
+  bool acc = accumulate_first;
+  for (int k = 0; k < k_red / 8; ++k) {
+    const uint32_t aoff = static_cast<uint32_t>(k) * 256u, woff = static_cast<uint32_t>(k) * w_grp;
+    const uint64_t ah = make_desc(a_hi + aoff, 128, a_sbo), al = make_desc(a_lo + aoff, 128, a_sbo);
+    const uint64_t bh = make_desc(w_hi + woff, w_grp, 128), bl = make_desc(w_lo + woff, w_grp, 128);
+    mma_tf32(d_tmem, al, bh, idesc, acc);
+    mma_tf32(d_tmem, ah, bl, idesc, true);
+    mma_tf32(d_tmem, ah, bh, idesc, true);
+    acc = true;
+  }
+}
+
+// D[64, N] (+)= P^T[64, 128] * Q[128, N]: P and Q are canonical tiles of 128 rows (samples) with p_cols / q_cols
+// columns, both read MN-major (reduction over the 128 rows).  Rows of D at or beyond p_cols are meaningless (the
+// descriptor walks past P's columns into the next row group) and are ignored by the caller.  This is the weight
+// gradient dW = dOut^T * In.  3xTF32.  One thread.
+__device__ __forceinline__ void issue_gemm_tn(uint32_t d_tmem, uint32_t p_hi, uint32_t p_lo, int p_cols, uint32_t q_hi,
+                                              uint32_t q_lo, int q_cols, bool accumulate_first) {
+  const uint32_t idesc = make_idesc_m(64, q_cols, 1, 1);
+  const uint32_t p_grp = static_cast<uint32_t>(p_cols / 4) * 128u, q_grp = static_cast<uint32_t>(q_cols / 4) * 128u;
+  bool acc = accumulate_first;
+  for (int k = 0; k < kRows / 8; ++k) {
+    const uint32_t poff = static_cast<uint32_t>(k) * p_grp, qoff = static_cast<uint32_t>(k) * q_grp;
+    const uint64_t ph = make_desc(p_hi + poff, p_grp, 128), pl = make_desc(p_lo + poff, p_grp, 128);
+    const uint64_t qh = make_desc(q_hi + qoff, q_grp, 128), ql = make_desc(q_lo + qoff, q_grp, 128);
+    mma_tf32(d_tmem, pl, qh, idesc, acc);
+    mma_tf32(d_tmem, ph, ql, idesc, true);
+    mma_tf32(d_tmem, ph, qh, idesc, true);
+    acc = true;
+  }
+}
+
+// After the call lane j holds the sum over the warp's 32 lanes of v[j] (31 shuffles).
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      const bool upper = (lane & s) != 0;
+      const float send = upper ? v[i] : v[i + s];
+      const float keep = upper ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(kFull, send, s);
+    }
+  }
+  return v[0];
+}
+
+}  // namespace tc
+}  // namespace nrb

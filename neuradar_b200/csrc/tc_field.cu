@@ -187,6 +187,279 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   if (warp == 0) tmem_free<kTmemCols>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Backward of the fused field MLP.  Per 128-sample tile and per layer (last to first) two GEMM chains are issued on
+// the tensor cores from the SAME shared-memory tiles:
+//     dW_l (+)= delta_l^T * in_l        M = 64 (rows >= out_l ignored), N = in_l, reduction over the 128 samples,
+//                                        accumulated in TMEM across ALL tiles of the CTA and flushed once at the end;
+//     dIn_l  = delta_l * W_l            M = 128, N = in_l, reduction over out_l (W_l read MN-major as staged).
+// Bias gradients are column sums of delta_l (31-shuffle transpose-reduce per warp) kept in shared memory.
+struct FieldBwdIn {
+  const float* x;     // [M,32] hash features (input of the forward pass)
+  const float* h1;    // saved activations, [M,32] each
+  const float* emb;
+  const float* g1;
+  const float* g2;
+  const float* sh;    // [N_rays,16]
+  const float* sdf;   // [M]
+  const float* alpha; // [M]
+  const float* dfeature;  // [M,32]
+  const float* dsdf;      // [M] or null
+  const float* dalpha;    // [M] or null
+};
+
+struct FieldBwdOut {
+  float* dx;      // [M,32] or null
+  float* dw[5];   // accumulated into
+  float* db[5];
+  float* dbeta;   // [1]: d loss / d(|beta| + beta_min), accumulated into
+};
+
+constexpr int kBwdTmemCols = 256;
+__device__ constexpr int kDwCol[5] = {208, 176, 128, 96, 64};  // TMEM column of each layer's dW accumulator
+
+struct FieldBwdSmem {
+  static constexpr int bias_unused = field_w_hi(5);
+  static constexpr int d_hi = field_w_hi(5);
+  static constexpr int d_lo = d_hi + kRows * 48 * 4;
+  static constexpr int a_hi = d_lo + kRows * 48 * 4;
+  static constexpr int a_lo = a_hi + kRows * 48 * 4;
+  static constexpr int dbacc = a_lo + kRows * 48 * 4;  // [4 warps][5 layers][48]
+  static constexpr int mbar = dbacc + 4 * 5 * 48 * 4;
+  static constexpr int tmem = mbar + 8;
+  static constexpr int total = tmem + 8;
+};
+
+// TMEM lane that holds row r of an M = 64 accumulator (cta_group::1): 16 rows per 32-lane quarter.
+__device__ __forceinline__ int m64_row_of_lane(int lane128) {
+  const int q = lane128 >> 5, i = lane128 & 31;
+  return i < 16 ? q * 16 + i : -1;
+}
+
+__global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_constant__ FieldParams prm,
+                                                                 const __grid_constant__ FieldBwdIn in,
+                                                                 const __grid_constant__ FieldBwdOut out,
+                                                                 int samples_per_ray, int64_t M) {
+  extern __shared__ __align__(128) char smem[];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  char* d_hi = smem + FieldBwdSmem::d_hi;
+  char* d_lo = smem + FieldBwdSmem::d_lo;
+  char* a_hi = smem + FieldBwdSmem::a_hi;
+  char* a_lo = smem + FieldBwdSmem::a_lo;
+  float* dbacc = reinterpret_cast<float*>(smem + FieldBwdSmem::dbacc);
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FieldBwdSmem::mbar);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldBwdSmem::tmem);
+
+  for (int l = 0; l < 5; ++l)
+    stage_weight_split(prm.w[l], kOut[l], kN[l], kK[l], smem + field_w_hi(l), smem + field_w_lo(l));
+  for (int i = t; i < 4 * 5 * 48; i += kRows) dbacc[i] = 0.0f;
+  if (warp == 0) tmem_alloc<kBwdTmemCols>(tmem_slot);
+  if (t == 0) mbar_init(mbar, 1);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t d_hi_u = smem_u32(d_hi), d_lo_u = smem_u32(d_lo), a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo);
+  const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
+  uint32_t phase = 0;
+  bool first = true;
+  float dbeta_acc = 0.0f;
+  float* my_db = dbacc + warp * 5 * 48;
+
+  auto run_layer = [&](int l, int dcols, int acols, int kred) {
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    if (t == 0) {
+      fence_after_sync();
+      issue_gemm_tn(tmem_base + kDwCol[l], d_hi_u, d_lo_u, dcols, a_hi_u, a_lo_u, acols, !first);
+      issue_gemm_a_kmajor_b_mnmajor(tmem_base, d_hi_u, d_lo_u, dcols, smem_u32(smem + field_w_hi(l)),
+                                    smem_u32(smem + field_w_lo(l)), kK[l], kred, false);
+      mma_commit(mbar);
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1;
+    fence_after_sync();
+  };
+
+  const int64_t tiles = (M + kRows - 1) / kRows;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row = tile * kRows + t;
+    const bool ok = row < M;
+    const int64_t rr = ok ? row : (M - 1);
+    float delta[32], act[32], tmp[32];
+    // ---- layer 4 (mlp_feature.layers.2): delta = d feature
+    load_row32(in.dfeature + rr * 32, delta);
+    if (!ok) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) delta[j] = 0.0f;
+    }
+    float demb[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) demb[j] = delta[j];  // residual branch
+    load_row32(in.g2 + rr * 32, act);
+    store_row_split<32>(d_hi, d_lo, t, delta);
+    store_row_split<32>(a_hi, a_lo, t, act);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
+    my_db[4 * 48 + lane] += warp_column_sums(tmp, lane);
+    run_layer(4, 32, 32, 32);
+    tmem_load_row<32>(tmem_base, warp, 0, delta);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
+    // ---- layer 3 (mlp_feature.layers.1)
+    load_row32(in.g1 + rr * 32, act);
+    store_row_split<32>(d_hi, d_lo, t, delta);
+    store_row_split<32>(a_hi, a_lo, t, act);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
+    my_db[3 * 48 + lane] += warp_column_sums(tmp, lane);
+    run_layer(3, 32, 32, 32);
+    tmem_load_row<32>(tmem_base, warp, 0, delta);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
+    // ---- layer 2 (mlp_feature.layers.0): input [emb | sh]
+    {
+      float in48[48];
+      load_row32(in.emb + rr * 32, act);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) in48[j] = act[j];
+      const float4* shp = reinterpret_cast<const float4*>(in.sh + (rr / samples_per_ray) * 16);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 q = __ldg(shp + c);
+        in48[32 + 4 * c] = q.x;
+        in48[32 + 4 * c + 1] = q.y;
+        in48[32 + 4 * c + 2] = q.z;
+        in48[32 + 4 * c + 3] = q.w;
+      }
+      store_row_split<32>(d_hi, d_lo, t, delta);
+      store_row_split<48>(a_hi, a_lo, t, in48);
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
+    my_db[2 * 48 + lane] += warp_column_sums(tmp, lane);
+    run_layer(2, 32, 48, 32);
+    {
+      float din[48];
+      tmem_load_row<48>(tmem_base, warp, 0, din);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) demb[j] += din[j];  // the SH part of the input carries no gradient
+    }
+    // ---- layer 1 (mlp_geo.layers.1): delta = [d sdf | d emb], padded to 48 columns
+    float dsdf_v = 0.0f;
+    if (ok) {
+      const float a = __ldg(in.alpha + row), sd = __ldg(in.sdf + row);
+      const float da = in.dalpha != nullptr ? __ldg(in.dalpha + row) : 0.0f;
+      const float s = a * (1.0f - a);
+      dsdf_v = (in.dsdf != nullptr ? __ldg(in.dsdf + row) : 0.0f) - da * beta * s;
+      dbeta_acc -= da * sd * s;
+    }
+    {
+      float d48[48];
+      d48[0] = dsdf_v;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) d48[1 + j] = demb[j];
+#pragma unroll
+      for (int j = 33; j < 48; ++j) d48[j] = 0.0f;
+      load_row32(in.h1 + rr * 32, act);
+      store_row_split<48>(d_hi, d_lo, t, d48);
+      store_row_split<32>(a_hi, a_lo, t, act);
+    }
+    {
+      const float s0 = warp_sum(dsdf_v);
+      if (lane == 0) my_db[1 * 48 + 0] += s0;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) tmp[j] = demb[j];
+      my_db[1 * 48 + 1 + lane] += warp_column_sums(tmp, lane);
+    }
+    run_layer(1, 48, 32, 40);
+    tmem_load_row<32>(tmem_base, warp, 0, delta);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
+    // ---- layer 0 (mlp_geo.layers.0)
+    load_row32(in.x + rr * 32, act);
+    store_row_split<32>(d_hi, d_lo, t, delta);
+    store_row_split<32>(a_hi, a_lo, t, act);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
+    my_db[0 * 48 + lane] += warp_column_sums(tmp, lane);
+    run_layer(0, 32, 32, 32);
+    if (out.dx != nullptr) {
+      tmem_load_row<32>(tmem_base, warp, 0, delta);
+      if (ok) store_row32(out.dx + row * 32, delta);
+    }
+    first = false;
+  }
+  // ---- flush: weight gradients from TMEM, bias gradients from shared memory, beta
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (!first) {
+    const int r = m64_row_of_lane(t);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      float acc48[48];
+      tmem_load_row<48>(tmem_base, warp, kDwCol[l], acc48);
+      if (r >= 0 && r < kOut[l] && out.dw[l] != nullptr) {
+        for (int k = 0; k < kK[l]; ++k) atomicAdd(out.dw[l] + r * kK[l] + k, acc48[k]);
+      }
+    }
+    for (int i = t; i < 5 * 48; i += kRows) {
+      const int l = i / 48, j = i - l * 48;
+      if (j < kOut[l] && out.db[l] != nullptr)
+        atomicAdd(out.db[l] + j, dbacc[i] + dbacc[5 * 48 + i] + dbacc[2 * 5 * 48 + i] + dbacc[3 * 5 * 48 + i]);
+    }
+    const float s = warp_sum(dbeta_acc);
+    if (lane == 0 && out.dbeta != nullptr) atomicAdd(out.dbeta, s);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<kBwdTmemCols>(tmem_base);
+}
+
+// Probe of the TMEM data-path layout of an M = 64 accumulator: D = P^T Q with P[s][j] = (s == 0) * (j + 1) and
+// Q[s][n] = (s == 0), so row j of D is the constant j + 1; dump[lane][col] tells which lane holds which row.
+__global__ void __launch_bounds__(kRows) tc_probe_m64_kernel(float* __restrict__ dump) {
+  extern __shared__ __align__(128) char smem[];
+  const int t = threadIdx.x, warp = t >> 5;
+  char* p_hi = smem;
+  char* p_lo = p_hi + kRows * 32 * 4;
+  char* q_hi = p_lo + kRows * 32 * 4;
+  char* q_lo = q_hi + kRows * 32 * 4;
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(q_lo + kRows * 32 * 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
+  float p[32], q[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    p[j] = (t == 0) ? static_cast<float>(j + 1) : 0.0f;
+    q[j] = (t == 0) ? 1.0f : 0.0f;
+  }
+  store_row_split<32>(p_hi, p_lo, t, p);
+  store_row_split<32>(q_hi, q_lo, t, q);
+  if (warp == 0) tmem_alloc<64>(tmem_slot);
+  if (t == 0) mbar_init(mbar, 1);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  // clear the accumulator region first so that untouched lanes read as a sentinel
+  if (t == 0) {
+    issue_gemm_tn(tmem_base, smem_u32(p_hi), smem_u32(p_lo), 32, smem_u32(q_hi), smem_u32(q_lo), 32, false);
+    mma_commit(mbar);
+  }
+  mbar_wait(mbar, 0);
+  fence_after_sync();
+  float acc[32];
+  tmem_load_row<32>(tmem_base, warp, 0, acc);
+  for (int j = 0; j < 32; ++j) dump[t * 32 + j] = acc[j];
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<64>(tmem_base);
+}
+
 // Single linear layer y = x W^T + b (optionally ReLU) through the same building blocks: unit test of the descriptor
 // and layout conventions.  K in {32, 48}, N (padded) in {32, 48}.
 __global__ void __launch_bounds__(kRows) tc_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -301,4 +574,47 @@ extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const
   field_mlp_fwd_kernel<<<grid, tc::kRows, FieldSmem::total, static_cast<cudaStream_t>(stream)>>>(
       prm, sv, x, sh, samples_per_ray, M, feature, sdf, alpha);
   return finish_launch("nrb_field_mlp_fwd");
+}
+
+extern "C" int nrb_tc_probe_m64(float* dump, nrb_stream_t stream) {
+  NRB_REQUIRE(dump != nullptr, NRB_ERR_BAD_ARG, "nrb_tc_probe_m64: null pointer");
+  const size_t smem = 4 * tc::kRows * 32 * 4 + 16;
+  cudaError_t e = cudaFuncSetAttribute(tc_probe_m64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_probe_m64: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  tc_probe_m64_kernel<<<1, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(dump);
+  return finish_launch("nrb_tc_probe_m64");
+}
+
+extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
+                                 int32_t samples_per_ray, int64_t M, nrb_stream_t stream) {
+  NRB_REQUIRE(p && in && out && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: null pointer or bad size");
+  NRB_REQUIRE(in->x && in->h1 && in->emb && in->g1 && in->g2 && in->sh && in->sdf && in->alpha && in->dfeature,
+              NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: a required input is null");
+  for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: weights[%d] is null", l);
+  NRB_REQUIRE(p->beta != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: beta is null");
+  NRB_REQUIRE(aligned16(in->x) && aligned16(in->h1) && aligned16(in->emb) && aligned16(in->g1) && aligned16(in->g2) &&
+                  aligned16(in->sh) && aligned16(in->dfeature) && (out->dx == nullptr || aligned16(out->dx)),
+              NRB_ERR_ALIGNMENT, "nrb_field_mlp_bwd: row-major [M,32] arrays must be 16-byte aligned");
+  if (M == 0) return NRB_OK;
+  FieldParams prm;
+  for (int l = 0; l < 5; ++l) {
+    prm.w[l] = p->weights[l];
+    prm.b[l] = p->biases[l];
+  }
+  prm.beta = p->beta;
+  prm.beta_min = p->beta_min;
+  FieldBwdIn bi{in->x, in->h1, in->emb, in->g1, in->g2, in->sh, in->sdf, in->alpha, in->dfeature, in->dsdf, in->dalpha};
+  FieldBwdOut bo;
+  bo.dx = out->dx;
+  for (int l = 0; l < 5; ++l) {
+    bo.dw[l] = out->dweights[l];
+    bo.db[l] = out->dbiases[l];
+  }
+  bo.dbeta = out->dbeta;
+  cudaError_t e = cudaFuncSetAttribute(field_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwdSmem::total);
+  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
+  field_mlp_bwd_kernel<<<grid, tc::kRows, FieldBwdSmem::total, static_cast<cudaStream_t>(stream)>>>(prm, bi, bo, samples_per_ray, M);
+  return finish_launch("nrb_field_mlp_bwd");
 }

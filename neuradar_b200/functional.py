@@ -317,6 +317,79 @@ def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequ
     return feature, sdf, alpha, saved
 
 
+def tc_probe_m64() -> Tensor:
+    """[128 lanes, 32 columns] dump of an M = 64 tcgen05 accumulator whose row j holds j + 1 (layout probe)."""
+    dump = torch.full((128, 32), -1.0, device="cuda", dtype=torch.float32)
+    _lib.call("nrb_tc_probe_m64", ptr(dump), stream_ptr())
+    return dump
+
+
+class _FieldMlp(torch.autograd.Function):
+    """Fused tensor-core field MLP with its hand-written backward.  Inputs: x [M,32], sh [N,16], beta [1], then the
+    five weights and five biases; outputs feature [M,32], sdf [M], alpha [M]."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, sh, samples_per_ray: int, beta_min: float, beta, *params):
+        x, sh, beta = f32c(x), f32c(sh.detach()), f32c(beta)
+        weights = [f32c(w) for w in params[:5]]
+        biases = [None if b is None else f32c(b) for b in params[5:]]
+        M, dev = x.shape[0], x.device
+        feature = torch.empty((M, 32), device=dev, dtype=torch.float32)
+        sdf = torch.empty((M,), device=dev, dtype=torch.float32)
+        alpha = torch.empty((M,), device=dev, dtype=torch.float32)
+        train = any(ctx.needs_input_grad)
+        sv = _lib.FieldSaved()
+        saved = []
+        if train:
+            saved = [torch.empty((M, 32), device=dev, dtype=torch.float32) for _ in range(4)]
+            sv.h1, sv.emb, sv.g1, sv.g2 = (ptr(t) for t in saved)
+        m = _field_struct(weights, biases, beta, beta_min)
+        _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
+                  ptr(alpha), C.byref(sv), stream_ptr())
+        if train:
+            ctx.save_for_backward(x, sh, beta, sdf, alpha, *saved, *weights, *[b for b in biases if b is not None])
+            ctx.has_bias = [b is not None for b in biases]
+            ctx.samples_per_ray, ctx.beta_min = int(samples_per_ray), float(beta_min)
+        return feature, sdf, alpha
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dfeature, dsdf, dalpha):
+        t = ctx.saved_tensors
+        x, sh, beta, sdf, alpha, h1, emb, g1, g2 = t[:9]
+        weights = list(t[9:14])
+        rest = list(t[14:])
+        biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+        M = x.shape[0]
+        dfeature = torch.zeros_like(h1) if dfeature is None else f32c(dfeature)
+        dsdf = None if dsdf is None else f32c(dsdf)
+        dalpha = None if dalpha is None else f32c(dalpha)
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dws = [torch.zeros_like(w) for w in weights]
+        dbs = [None if b is None else torch.zeros_like(b) for b in biases]
+        dbeta_eff = torch.zeros((1,), device=x.device, dtype=torch.float32)
+        m = _field_struct(weights, biases, beta, ctx.beta_min)
+        bi = _lib.FieldBwdIn()
+        bi.x, bi.h1, bi.emb, bi.g1, bi.g2, bi.sh = ptr(x), ptr(h1), ptr(emb), ptr(g1), ptr(g2), ptr(sh)
+        bi.sdf, bi.alpha, bi.dfeature, bi.dsdf, bi.dalpha = ptr(sdf), ptr(alpha), ptr(dfeature), ptr(dsdf), ptr(dalpha)
+        bo = _lib.FieldBwdOut()
+        bo.dx = ptr(dx)
+        for i in range(5):
+            bo.dweights[i] = ptr(dws[i])
+            bo.dbiases[i] = ptr(dbs[i])
+        bo.dbeta = ptr(dbeta_eff)
+        _lib.call("nrb_field_mlp_bwd", C.byref(m), C.byref(bi), C.byref(bo), ctx.samples_per_ray, M, stream_ptr())
+        dbeta = dbeta_eff * torch.sign(beta)  # d(|beta| + beta_min) / d beta
+        return (dx, None, None, None, dbeta.view_as(beta), *dws, *dbs)
+
+
+def field_mlp(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]],
+              beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """NeuRADField after the hash grid, fused on the tensor cores: (feature [M,32], sdf [M], alpha [M])."""
+    return _FieldMlp.apply(x, sh, samples_per_ray, beta_min, beta, *weights, *biases)
+
+
 def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:
     """16 real SH basis values of directions [M,3]; no gradient (reference: torch.no_grad)."""
     d = f32c(directions.detach())

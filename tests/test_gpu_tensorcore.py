@@ -68,3 +68,44 @@ def test_field_mlp_forward(N, S):
     assert float((alpha.cpu() - ra).abs().max()) <= 2e-5
     h1 = torch.relu(torch.nn.functional.linear(x, ws[0], bs[0]))
     assert rel_err(saved[0], h1) <= 1e-5
+
+
+def test_m64_accumulator_layout():
+    """The backward kernel relies on row r of an M=64 accumulator living in TMEM lane (r/16)*32 + r%16."""
+    from neuradar_b200 import functional as Fn
+
+    dump = Fn.tc_probe_m64().cpu()
+    for lane in range(128):
+        q, i = divmod(lane, 32)
+        if i < 16:
+            assert torch.all(dump[lane] == float(q * 16 + i + 1)), (lane, dump[lane, :4])
+
+
+@pytest.mark.parametrize("N,S", [(8, 48), (600, 48), (129, 33)])
+def test_field_mlp_backward(N, S):
+    from neuradar_b200 import functional as Fn
+
+    x, sh, ws, bs, beta = _field_inputs(N, S, seed=7 * N + S)
+    g = torch.Generator().manual_seed(1)
+    M = N * S
+    gf, gs, ga = torch.randn((M, 32), generator=g), torch.randn((M,), generator=g), torch.randn((M,), generator=g)
+    # reference
+    xr = x.clone().requires_grad_(True)
+    wr = [w.clone().requires_grad_(True) for w in ws]
+    br = [b.clone().requires_grad_(True) for b in bs]
+    betar = beta.clone().requires_grad_(True)
+    rf, rs, ra = _field_ref(xr, sh, S, wr, br, betar)
+    ((rf * gf).sum() + (rs * gs).sum() + (ra * ga).sum()).backward()
+    # kernel
+    xd = x.to(DEV).requires_grad_(True)
+    wd = [w.to(DEV).requires_grad_(True) for w in ws]
+    bd = [b.to(DEV).requires_grad_(True) for b in bs]
+    betad = beta.to(DEV).requires_grad_(True)
+    f, s_, a = Fn.field_mlp(xd, sh.to(DEV), S, wd, bd, betad, 1e-4)
+    assert rel_err(f, rf) <= 1e-5
+    ((f * gf.to(DEV)).sum() + (s_ * gs.to(DEV)).sum() + (a * ga.to(DEV)).sum()).backward()
+    assert rel_err(xd.grad, xr.grad) <= 2e-5
+    for k in range(5):
+        assert rel_err(wd[k].grad, wr[k].grad) <= 2e-5, f"dW{k}"
+        assert rel_err(bd[k].grad, br[k].grad) <= 2e-5, f"db{k}"
+    assert rel_err(betad.grad, betar.grad) <= 2e-5
