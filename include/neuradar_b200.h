@@ -170,8 +170,10 @@ typedef struct {
 } nrb_field_bwd_out_t;
 int nrb_field_mlp_bwd(const nrb_field_mlp_t* mlp, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
                       int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
-/* Debug: dumps [128 lanes][32 columns] of an M = 64 tcgen05 accumulator whose row j holds the constant j + 1. */
-int nrb_tc_probe_m64(float* dump, nrb_stream_t stream);
+/* Debug probe of the UMMA descriptor conventions: P, Q [128,32] are staged as canonical tiles, a chain of tf32 MMAs
+ * is issued with cfg = {a_major, b_major, M, N, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps} (host ints) and the
+ * [128 lanes][32 columns] accumulator block is written to dump. */
+int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11, float* dump, nrb_stream_t stream);
 /* One linear layer y = x W^T + b (optional ReLU) through the same tcgen05 building blocks (K = 32 or 48,
  * n_out <= 48): the unit test of the descriptor / layout conventions. */
 int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,

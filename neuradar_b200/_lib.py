@@ -114,7 +114,7 @@ SIGNATURES = {
     "nrb_field_mlp_fwd": [C.POINTER(FieldMlp), _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(FieldSaved), _P],
     "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],
     "nrb_field_mlp_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldBwdIn), C.POINTER(FieldBwdOut), _I32, _I64, _P],
-    "nrb_tc_probe_m64": [_P, _P],
+    "nrb_tc_probe": [_P, _P, C.POINTER(C.c_int32), _P, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
     "nrb_pdf_sample": [C.POINTER(Rays), Spacing, _P, _P, _I32, _P, _P, _I32, _F, _F, _P, _P, _P, _P, _P],
     "nrb_density_weights_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],

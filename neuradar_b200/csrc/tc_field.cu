@@ -419,9 +419,16 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   if (warp == 0) tmem_free<kBwdTmemCols>(tmem_base);
 }
 
-// Probe of the TMEM data-path layout of an M = 64 accumulator: D = P^T Q with P[s][j] = (s == 0) * (j + 1) and
-// Q[s][n] = (s == 0), so row j of D is the constant j + 1; dump[lane][col] tells which lane holds which row.
-__global__ void __launch_bounds__(kRows) tc_probe_m64_kernel(float* __restrict__ dump) {
+// Generic probe of descriptor conventions: P and Q are [128,32] row-major host-provided matrices staged as canonical
+// tiles; one chain of `ksteps` tf32 MMAs is issued with caller-chosen majors, M, N, LBO/SBO and per-step address
+// advances; the [128 lanes][32 columns] accumulator block is dumped.
+struct ProbeCfg {
+  int a_major, b_major, m, n;
+  int a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps;
+};
+
+__global__ void __launch_bounds__(kRows) tc_probe_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                                                         ProbeCfg cfg, float* __restrict__ dump) {
   extern __shared__ __align__(128) char smem[];
   const int t = threadIdx.x, warp = t >> 5;
   char* p_hi = smem;
@@ -431,11 +438,8 @@ __global__ void __launch_bounds__(kRows) tc_probe_m64_kernel(float* __restrict__
   uint64_t* mbar = reinterpret_cast<uint64_t*>(q_lo + kRows * 32 * 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 1);
   float p[32], q[32];
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    p[j] = (t == 0) ? static_cast<float>(j + 1) : 0.0f;
-    q[j] = (t == 0) ? 1.0f : 0.0f;
-  }
+  load_row32(P + t * 32, p);
+  load_row32(Q + t * 32, q);
   store_row_split<32>(p_hi, p_lo, t, p);
   store_row_split<32>(q_hi, q_lo, t, q);
   if (warp == 0) tmem_alloc<64>(tmem_slot);
@@ -445,9 +449,13 @@ __global__ void __launch_bounds__(kRows) tc_probe_m64_kernel(float* __restrict__
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  // clear the accumulator region first so that untouched lanes read as a sentinel
   if (t == 0) {
-    issue_gemm_tn(tmem_base, smem_u32(p_hi), smem_u32(p_lo), 32, smem_u32(q_hi), smem_u32(q_lo), 32, false);
+    const uint32_t idesc = make_idesc_m(cfg.m, cfg.n, cfg.a_major, cfg.b_major);
+    for (int k = 0; k < cfg.ksteps; ++k) {
+      const uint64_t ad = make_desc(smem_u32(p_hi) + k * cfg.a_step, cfg.a_lbo, cfg.a_sbo);
+      const uint64_t bd = make_desc(smem_u32(q_hi) + k * cfg.b_step, cfg.b_lbo, cfg.b_sbo);
+      mma_tf32(tmem_base, ad, bd, idesc, k > 0);
+    }
     mma_commit(mbar);
   }
   mbar_wait(mbar, 0);
@@ -576,13 +584,14 @@ extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const
   return finish_launch("nrb_field_mlp_fwd");
 }
 
-extern "C" int nrb_tc_probe_m64(float* dump, nrb_stream_t stream) {
-  NRB_REQUIRE(dump != nullptr, NRB_ERR_BAD_ARG, "nrb_tc_probe_m64: null pointer");
+extern "C" int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11, float* dump, nrb_stream_t stream) {
+  NRB_REQUIRE(P && Q && cfg11 && dump, NRB_ERR_BAD_ARG, "nrb_tc_probe: null pointer");
+  ProbeCfg c{cfg11[0], cfg11[1], cfg11[2], cfg11[3], cfg11[4], cfg11[5], cfg11[6], cfg11[7], cfg11[8], cfg11[9], cfg11[10]};
   const size_t smem = 4 * tc::kRows * 32 * 4 + 16;
-  cudaError_t e = cudaFuncSetAttribute(tc_probe_m64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_probe_m64: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  tc_probe_m64_kernel<<<1, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(dump);
-  return finish_launch("nrb_tc_probe_m64");
+  cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_probe: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  tc_probe_kernel<<<1, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(P, Q, c, dump);
+  return finish_launch("nrb_tc_probe");
 }
 
 extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,

@@ -317,10 +317,12 @@ def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequ
     return feature, sdf, alpha, saved
 
 
-def tc_probe_m64() -> Tensor:
-    """[128 lanes, 32 columns] dump of an M = 64 tcgen05 accumulator whose row j holds j + 1 (layout probe)."""
-    dump = torch.full((128, 32), -1.0, device="cuda", dtype=torch.float32)
-    _lib.call("nrb_tc_probe_m64", ptr(dump), stream_ptr())
+def tc_probe(P: Tensor, Q: Tensor, cfg: Sequence[int]) -> Tensor:
+    """Descriptor-convention probe (see nrb_tc_probe): returns the [128, 32] accumulator dump."""
+    P, Q = f32c(P), f32c(Q)
+    dump = torch.full((128, 32), -1.0, device=P.device, dtype=torch.float32)
+    arr = (C.c_int32 * 11)(*[int(v) for v in cfg])
+    _lib.call("nrb_tc_probe", ptr(P), ptr(Q), arr, ptr(dump), stream_ptr())
     return dump
 
 
