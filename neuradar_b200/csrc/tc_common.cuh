@@ -199,20 +199,19 @@ __device__ __forceinline__ uint32_t make_idesc_m(int m, int n, int a_mn_major, i
          (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// D[128, N] (+)= A[128, Kred] * W[Kred, N]: A is a K-major canonical tile with `a_cols` columns (reduction over its
-// columns), W is the canonical tile of a row-major [rows >= Kred][N] matrix read as an MN-major B operand (reduction
-// over its ROWS).  This is dIn = dOut * W with W staged exactly as for the forward pass.  3xTF32.  One thread.
-__device__ __forceinline__ void issue_gemm_a_kmajor_b_mnmajor(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, int a_cols,
-                                                              uint32_t w_hi, uint32_t w_lo, int w_cols, int k_red,
-                                                              bool accumulate_first) {
-  const uint32_t idesc = make_idesc_m(128, w_cols, 0, 1);
-  const uint32_t a_sbo = static_cast<uint32_t>(a_cols / 4) * 128u;
-  const uint32_t w_grp = static_cast<uint32_t>(w_cols / 4) * 128u;  // next 8 rows of W
+// General K-major x K-major chain: D[m, n] (+)= A[m, k_red] * B[n, k_red]^T, A / B canonical tiles with a_cols / b_cols
+// columns (>= k_red), m in {64, 128}.  3xTF32.  One thread.
+// (MN-major operands were measured to produce all-zero accumulators with kind::tf32 and SWIZZLE_NONE on B200 for every
+//  LBO/SBO assignment, so the backward pass stages explicit transposes instead; see tools_tc_probe.py.)
+__device__ __forceinline__ void issue_gemm(uint32_t d_tmem, int m, int n, uint32_t a_hi, uint32_t a_lo, int a_cols,
+                                           uint32_t b_hi, uint32_t b_lo, int b_cols, int k_red, bool accumulate_first) {
+  const uint32_t idesc = make_idesc_m(m, n, 0, 0);
+  const uint32_t a_sbo = static_cast<uint32_t>(a_cols / 4) * 128u, b_sbo = static_cast<uint32_t>(b_cols / 4) * 128u;
   bool acc = accumulate_first;
   for (int k = 0; k < k_red / 8; ++k) {
-    const uint32_t aoff = static_cast<uint32_t>(k) * 256u, woff = static_cast<uint32_t>(k) * w_grp;
-    const uint64_t ah = make_desc(a_hi + aoff, 128, a_sbo), al = make_desc(a_lo + aoff, 128, a_sbo);
-    const uint64_t bh = make_desc(w_hi + woff, w_grp, 128), bl = make_desc(w_lo + woff, w_grp, 128);
+    const uint32_t koff = static_cast<uint32_t>(k) * 256u;
+    const uint64_t ah = make_desc(a_hi + koff, 128, a_sbo), al = make_desc(a_lo + koff, 128, a_sbo);
+    const uint64_t bh = make_desc(b_hi + koff, 128, b_sbo), bl = make_desc(b_lo + koff, 128, b_sbo);
     mma_tf32(d_tmem, al, bh, idesc, acc);
     mma_tf32(d_tmem, ah, bl, idesc, true);
     mma_tf32(d_tmem, ah, bh, idesc, true);
@@ -220,24 +219,55 @@ __device__ __forceinline__ void issue_gemm_a_kmajor_b_mnmajor(uint32_t d_tmem, u
   }
 }
 
-// D[64, N] (+)= P^T[64, 128] * Q[128, N]: P and Q are canonical tiles of 128 rows (samples) with p_cols / q_cols
-// columns, both read MN-major (reduction over the 128 rows).  Rows of D at or beyond p_cols are meaningless (the
-// descriptor walks past P's columns into the next row group) and are ignored by the caller.  This is the weight
-// gradient dW = dOut^T * In.  3xTF32.  One thread.
-__device__ __forceinline__ void issue_gemm_tn(uint32_t d_tmem, uint32_t p_hi, uint32_t p_lo, int p_cols, uint32_t q_hi,
-                                              uint32_t q_lo, int q_cols, bool accumulate_first) {
-  const uint32_t idesc = make_idesc_m(64, q_cols, 1, 1);
-  const uint32_t p_grp = static_cast<uint32_t>(p_cols / 4) * 128u, q_grp = static_cast<uint32_t>(q_cols / 4) * 128u;
-  bool acc = accumulate_first;
-  for (int k = 0; k < kRows / 8; ++k) {
-    const uint32_t poff = static_cast<uint32_t>(k) * p_grp, qoff = static_cast<uint32_t>(k) * q_grp;
-    const uint64_t ph = make_desc(p_hi + poff, p_grp, 128), pl = make_desc(p_lo + poff, p_grp, 128);
-    const uint64_t qh = make_desc(q_hi + qoff, q_grp, 128), ql = make_desc(q_lo + qoff, q_grp, 128);
-    mma_tf32(d_tmem, pl, qh, idesc, acc);
-    mma_tf32(d_tmem, ph, ql, idesc, true);
-    mma_tf32(d_tmem, ph, qh, idesc, true);
-    acc = true;
+// Stage the TRANSPOSE of a row-major weight matrix w[n_rows][k_cols] as a canonical tile with k_cols rows and n_pad
+// columns (zero beyond n_rows), hi and lo halves.  Whole CTA.
+__device__ __forceinline__ void stage_weight_transposed_split(const float* __restrict__ w, int n_rows, int n_pad,
+                                                              int k_cols, char* hi_tile, char* lo_tile) {
+  for (int e = threadIdx.x; e < k_cols * n_pad; e += blockDim.x) {
+    const int r = e / n_pad, c = e - r * n_pad;  // tile row = input index, tile column = output index
+    const float v = (c < n_rows) ? __ldg(w + c * k_cols + r) : 0.0f;
+    const float h = tf32_hi(v);
+    const uint32_t off = tile_offset(r, c >> 2, n_pad) + (c & 3) * 4;
+    *reinterpret_cast<float*>(hi_tile + off) = h;
+    *reinterpret_cast<float*>(lo_tile + off) = v - h;
   }
+}
+
+// Transpose a canonical [128 rows x C cols] tile into a canonical [C rows x 128 cols] tile.  kSplit: the source holds
+// raw fp32 values that are split into hi / lo on the way; otherwise src_a / src_b are already the hi / lo halves and
+// are transposed one to one.  Whole CTA (128 threads); callers synchronise around it.
+template <bool kSplit>
+__device__ __forceinline__ void transpose_tile(const char* src_a, const char* src_b, int C, char* dst_hi, char* dst_lo) {
+  for (int e = threadIdx.x; e < C * 32; e += kRows) {
+    const int j = (e & 7) + 8 * (e >> 8);  // feature (source column, destination row)
+    const int c4 = (e >> 3) & 31;          // chunk of 4 samples (source rows 4*c4 .. 4*c4+3)
+    float a[4], b[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t off = tile_offset(4 * c4 + i, j >> 2, C) + (j & 3) * 4;
+      a[i] = *reinterpret_cast<const float*>(src_a + off);
+      if constexpr (!kSplit) b[i] = *reinterpret_cast<const float*>(src_b + off);
+    }
+    float4 h, l;
+    if constexpr (kSplit) {
+      h = make_float4(tf32_hi(a[0]), tf32_hi(a[1]), tf32_hi(a[2]), tf32_hi(a[3]));
+      l = make_float4(a[0] - h.x, a[1] - h.y, a[2] - h.z, a[3] - h.w);
+    } else {
+      h = make_float4(a[0], a[1], a[2], a[3]);
+      l = make_float4(b[0], b[1], b[2], b[3]);
+    }
+    const uint32_t doff = tile_offset(j, c4, kRows);
+    *reinterpret_cast<float4*>(dst_hi + doff) = h;
+    *reinterpret_cast<float4*>(dst_lo + doff) = l;
+  }
+}
+
+// Write one row (K values) of a canonical tile without splitting.
+template <int K>
+__device__ __forceinline__ void store_row_raw(char* tile, int row, const float (&v)[K]) {
+#pragma unroll
+  for (int c = 0; c < K / 4; ++c)
+    *reinterpret_cast<float4*>(tile + tile_offset(row, c, K)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
 // After the call lane j holds the sum over the warp's 32 lanes of v[j] (31 shuffles).

@@ -219,18 +219,22 @@ constexpr int kBwdTmemCols = 256;
 __device__ constexpr int kDwCol[5] = {208, 176, 128, 96, 64};  // TMEM column of each layer's dW accumulator
 
 struct FieldBwdSmem {
-  static constexpr int bias_unused = field_w_hi(5);
-  static constexpr int d_hi = field_w_hi(5);
+  // transposed weights (hi/lo) share the forward kernel's per-layer sizes: W_l^T is [in_l rows x out_l(pad) cols]
+  static constexpr int d_hi = field_w_hi(5);            // delta, [128 x 48] K-major (A of the data-gradient GEMM)
   static constexpr int d_lo = d_hi + kRows * 48 * 4;
-  static constexpr int a_hi = d_lo + kRows * 48 * 4;
-  static constexpr int a_lo = a_hi + kRows * 48 * 4;
-  static constexpr int dbacc = a_lo + kRows * 48 * 4;  // [4 warps][5 layers][48]
+  static constexpr int s_raw = d_lo + kRows * 48 * 4;   // layer input rows, [128 x 48] raw fp32 (transpose source)
+  static constexpr int dt_hi = s_raw + kRows * 48 * 4;  // delta^T, [48 x 128] (A of the weight-gradient GEMM)
+  static constexpr int dt_lo = dt_hi + 48 * kRows * 4;
+  static constexpr int at_hi = dt_lo + 48 * kRows * 4;  // input^T, [48 x 128] (B of the weight-gradient GEMM)
+  static constexpr int at_lo = at_hi + 48 * kRows * 4;
+  static constexpr int dbacc = at_lo + 48 * kRows * 4;  // [4 warps][5 layers][48]
   static constexpr int mbar = dbacc + 4 * 5 * 48 * 4;
   static constexpr int tmem = mbar + 8;
   static constexpr int total = tmem + 8;
 };
 
-// TMEM lane that holds row r of an M = 64 accumulator (cta_group::1): 16 rows per 32-lane quarter.
+// TMEM lane that holds row r of an M = 64 accumulator (cta_group::1): 16 rows per 32-lane quarter (measured with
+// tools_tc_probe.py: lane (r / 16) * 32 + r % 16).
 __device__ __forceinline__ int m64_row_of_lane(int lane128) {
   const int q = lane128 >> 5, i = lane128 & 31;
   return i < 16 ? q * 16 + i : -1;
@@ -244,14 +248,17 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   char* d_hi = smem + FieldBwdSmem::d_hi;
   char* d_lo = smem + FieldBwdSmem::d_lo;
-  char* a_hi = smem + FieldBwdSmem::a_hi;
-  char* a_lo = smem + FieldBwdSmem::a_lo;
+  char* s_raw = smem + FieldBwdSmem::s_raw;
+  char* dt_hi = smem + FieldBwdSmem::dt_hi;
+  char* dt_lo = smem + FieldBwdSmem::dt_lo;
+  char* at_hi = smem + FieldBwdSmem::at_hi;
+  char* at_lo = smem + FieldBwdSmem::at_lo;
   float* dbacc = reinterpret_cast<float*>(smem + FieldBwdSmem::dbacc);
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FieldBwdSmem::mbar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldBwdSmem::tmem);
 
   for (int l = 0; l < 5; ++l)
-    stage_weight_split(prm.w[l], kOut[l], kN[l], kK[l], smem + field_w_hi(l), smem + field_w_lo(l));
+    stage_weight_transposed_split(prm.w[l], kOut[l], kN[l], kK[l], smem + field_w_hi(l), smem + field_w_lo(l));
   for (int i = t; i < 4 * 5 * 48; i += kRows) dbacc[i] = 0.0f;
   if (warp == 0) tmem_alloc<kBwdTmemCols>(tmem_slot);
   if (t == 0) mbar_init(mbar, 1);
@@ -260,22 +267,28 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t d_hi_u = smem_u32(d_hi), d_lo_u = smem_u32(d_lo), a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo);
   const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
   uint32_t phase = 0;
   bool first = true;
   float dbeta_acc = 0.0f;
   float* my_db = dbacc + warp * 5 * 48;
 
+  // delta rows are in d_hi/d_lo (dcols columns), input rows in s_raw (acols columns): transpose both, then issue
+  //   dW_l (+)= delta^T in   (M = 64, N = acols, reduction over the 128 samples)   -> TMEM column kDwCol[l]
+  //   dIn   = delta W_l      (M = 128, N = acols, reduction over kred delta columns) -> TMEM column 0
   auto run_layer = [&](int l, int dcols, int acols, int kred) {
+    __syncthreads();
+    transpose_tile<false>(d_hi, d_lo, dcols, dt_hi, dt_lo);
+    transpose_tile<true>(s_raw, nullptr, acols, at_hi, at_lo);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (t == 0) {
       fence_after_sync();
-      issue_gemm_tn(tmem_base + kDwCol[l], d_hi_u, d_lo_u, dcols, a_hi_u, a_lo_u, acols, !first);
-      issue_gemm_a_kmajor_b_mnmajor(tmem_base, d_hi_u, d_lo_u, dcols, smem_u32(smem + field_w_hi(l)),
-                                    smem_u32(smem + field_w_lo(l)), kK[l], kred, false);
+      issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
+                 smem_u32(at_lo), kRows, kRows, !first);
+      issue_gemm(tmem_base, 128, acols, smem_u32(d_hi), smem_u32(d_lo), dcols, smem_u32(smem + field_w_hi(l)),
+                 smem_u32(smem + field_w_lo(l)), kN[l], kred, false);
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase);
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     for (int j = 0; j < 32; ++j) demb[j] = delta[j];  // residual branch
     load_row32(in.g2 + rr * 32, act);
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_split<32>(a_hi, a_lo, t, act);
+    store_row_raw<32>(s_raw, t, act);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[4 * 48 + lane] += warp_column_sums(tmp, lane);
@@ -311,7 +324,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     // ---- layer 3 (mlp_feature.layers.1)
     load_row32(in.g1 + rr * 32, act);
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_split<32>(a_hi, a_lo, t, act);
+    store_row_raw<32>(s_raw, t, act);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[3 * 48 + lane] += warp_column_sums(tmp, lane);
@@ -335,7 +348,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
         in48[32 + 4 * c + 3] = q.w;
       }
       store_row_split<32>(d_hi, d_lo, t, delta);
-      store_row_split<48>(a_hi, a_lo, t, in48);
+      store_row_raw<48>(s_raw, t, in48);
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
@@ -365,7 +378,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       for (int j = 33; j < 48; ++j) d48[j] = 0.0f;
       load_row32(in.h1 + rr * 32, act);
       store_row_split<48>(d_hi, d_lo, t, d48);
-      store_row_split<32>(a_hi, a_lo, t, act);
+      store_row_raw<32>(s_raw, t, act);
     }
     {
       const float s0 = warp_sum(dsdf_v);
@@ -381,7 +394,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     // ---- layer 0 (mlp_geo.layers.0)
     load_row32(in.x + rr * 32, act);
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_split<32>(a_hi, a_lo, t, act);
+    store_row_raw<32>(s_raw, t, act);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[0 * 48 + lane] += warp_column_sums(tmp, lane);
@@ -403,7 +416,9 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       float acc48[48];
       tmem_load_row<48>(tmem_base, warp, kDwCol[l], acc48);
       if (r >= 0 && r < kOut[l] && out.dw[l] != nullptr) {
-        for (int k = 0; k < kK[l]; ++k) atomicAdd(out.dw[l] + r * kK[l] + k, acc48[k]);
+#pragma unroll
+        for (int k = 0; k < 48; ++k)
+          if (k < kK[l]) atomicAdd(out.dw[l] + r * kK[l] + k, acc48[k]);
       }
     }
     for (int i = t; i < 5 * 48; i += kRows) {
