@@ -68,6 +68,7 @@ class NeuRADField(nn.Module):
         super().__init__()
         self.config = config
         self.implementation = implementation
+        self.use_tensor_cores = True
         if config.num_multisamples != 1:
             raise NotImplementedError("num_multisamples must be 1")
         self.hashgrid: NeuRADHashEncoding = config.grid.setup(dynamic_actors=actors, static_scale=static_scale)
@@ -94,19 +95,45 @@ class NeuRADField(nn.Module):
         if self.config.use_sdf:
             param_groups["fields"] += list(self.sdf_to_density.parameters())
 
+    def _tensor_core_path(self) -> bool:
+        """The fused tcgen05 kernel is built for NeuRadar's default field: 32 hash features, geometry MLP
+        32 -> 32 -> 33, feature MLP 48 -> 32 -> 32 -> 32, SDF head.  Other shapes run the generic MLP kernels."""
+        c = self.config
+        return (
+            self.use_tensor_cores
+            and c.use_sdf
+            and self.hashgrid.get_out_dim() == 32
+            and (c.geo_hidden_dim, c.geo_num_layers, c.nff_hidden_dim, c.nff_num_layers, c.nff_out_dim) == (32, 2, 32, 3, 32)
+        )
+
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
         if compute_normals:
             raise NotImplementedError("normals are not rendered on the NeuRadar path")
         rays, iv = ray_samples.per_ray()
         N, S = rays.num_rays, iv.num_samples
         features = self.hashgrid.encode_samples(rays, iv)
+        shape = ray_samples.shape if len(ray_samples.shape) == 2 else (N, S)
+        if self._tensor_core_path():
+            # everything after the hash grid in ONE tcgen05 kernel (and one for its backward)
+            sh = self.direction_encoding(get_normalized_directions(rays.directions))
+            geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
+            feature, sdf, alpha = F.field_mlp(
+                features, sh, S,
+                [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight],
+                [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias],
+                self.sdf_to_density.beta, float(self.sdf_to_density.beta_min),
+            )
+            return {
+                FieldHeadNames.FEATURE: feature.view(*shape, 32),
+                FieldHeadNames.SDF: sdf.view(*shape, 1),
+                FieldHeadNames.ALPHA: alpha.view(*shape, 1),
+            }
         geo = self.mlp_geo(features)
         geo_out, geo_embedding = torch.split(geo, [1, self.geo_feat_dim], dim=-1)
         # directions are per ray: evaluate the 16 SH values once per ray and broadcast over the samples
         sh = self.direction_encoding(get_normalized_directions(rays.directions))
         sh = sh[:, None, :].expand(N, S, 16).reshape(N * S, 16)
         feature = geo_embedding + self.mlp_feature(torch.cat([geo_embedding, sh], dim=-1))
-        shape = ray_samples.shape if len(ray_samples.shape) == 2 else (N, S)
         outputs = {FieldHeadNames.FEATURE: feature.view(*shape, self.config.nff_out_dim)}
         geo_out = geo_out.reshape(*shape, 1)
         if self.config.use_sdf:

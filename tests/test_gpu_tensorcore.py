@@ -78,6 +78,19 @@ def test_field_mlp_backward(N, S):
     g = torch.Generator().manual_seed(1)
     M = N * S
     gf, gs, ga = torch.randn((M, 32), generator=g), torch.randn((M,), generator=g), torch.randn((M,), generator=g)
+    # a ReLU whose pre-activation is within rounding of zero may legitimately switch between two fp32 evaluation
+    # orders; rows with such a unit get no upstream gradient so that the comparison is about arithmetic, not kinks
+    with torch.no_grad():
+        xd64 = x.double()
+        p0 = torch.nn.functional.linear(xd64, ws[0].double(), bs[0].double())
+        geo = torch.nn.functional.linear(torch.relu(p0), ws[1].double(), bs[1].double())
+        she = sh[:, None, :].expand(-1, S, -1).reshape(-1, 16).double()
+        p2 = torch.nn.functional.linear(torch.cat([geo[:, 1:], she], -1), ws[2].double(), bs[2].double())
+        p3 = torch.nn.functional.linear(torch.relu(p2), ws[3].double(), bs[3].double())
+        near_kink = (torch.cat([p0, p2, p3], -1).abs().min(dim=-1).values < 1e-5)
+    gf[near_kink] = 0
+    gs[near_kink] = 0
+    ga[near_kink] = 0
     # reference
     xr = x.clone().requires_grad_(True)
     wr = [w.clone().requires_grad_(True) for w in ws]
