@@ -7,6 +7,7 @@
 // feature matrix, and with the level fastest a warp writes (reads, in the backward pass) one contiguous
 // 32*F*4-byte span of it.  Each thread issues its 8 independent F-wide vector gathers before touching any of them.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -155,6 +156,14 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ G
   float w[8];
   corner_weights(c, w);
   const int copies = plan.copies[l];
+  if (copies > 1 && plan.r1[l] == 0) {  // replicas of the hashed level table
+    const unsigned warp_global = static_cast<unsigned>(gid >> 5);
+    float* rep = plan.scratch + plan.offset[l] +
+                 (static_cast<size_t>(warp_global % static_cast<unsigned>(copies)) << g.log2_size) * F;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) scatter_row<F>(rep, c.row[k], gr, w[k]);
+    return;
+  }
   if (copies > 1) {
     const int R1 = plan.r1[l];
     const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
@@ -186,13 +195,14 @@ __global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constan
   int l = 0;
   for (; l < g.num_levels; ++l) {
     if (plan.copies[l] <= 1) continue;
-    const int64_t nv = static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l];
-    if (v < nv) break;
-    v -= nv;
+    const int64_t nvl = plan.r1[l] > 0 ? static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l]
+                                       : (int64_t{1} << g.log2_size);
+    if (v < nvl) break;
+    v -= nvl;
   }
   if (l >= g.num_levels) return;
   const int R1 = plan.r1[l];
-  const int64_t nv = static_cast<int64_t>(R1) * R1 * R1;
+  const int64_t nv = R1 > 0 ? static_cast<int64_t>(R1) * R1 * R1 : (int64_t{1} << g.log2_size);
   const float* rep = plan.scratch + plan.offset[l] + v * F;
   float sum[F];
 #pragma unroll
@@ -207,9 +217,14 @@ __global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constan
 #pragma unroll
   for (int j = 0; j < F; ++j) any |= (sum[j] != 0.0f);
   if (!any) return;
-  const int ix = static_cast<int>(v % R1), iy = static_cast<int>((v / R1) % R1), iz = static_cast<int>(v / (R1 * R1));
-  const uint32_t row = (static_cast<uint32_t>(ix) ^ (static_cast<uint32_t>(iy) * kPrimeY) ^
-                        (static_cast<uint32_t>(iz) * kPrimeZ)) & ((1u << g.log2_size) - 1u);
+  uint32_t row;
+  if (R1 > 0) {
+    const int ix = static_cast<int>(v % R1), iy = static_cast<int>((v / R1) % R1), iz = static_cast<int>(v / (R1 * R1));
+    row = (static_cast<uint32_t>(ix) ^ (static_cast<uint32_t>(iy) * kPrimeY) ^ (static_cast<uint32_t>(iz) * kPrimeZ)) &
+          ((1u << g.log2_size) - 1u);
+  } else {
+    row = static_cast<uint32_t>(v);
+  }
   scatter_row<F>(dtable + (static_cast<size_t>(l) << g.log2_size) * F, row, sum, 1.0f);
 }
 
@@ -268,10 +283,22 @@ extern "C" int nrb_hash_indices(const nrb_grid_t* grid, const float* x, int64_t*
 
 // Replica plan: as many copies of a coarse level's lattice as it takes to bring its reductions per address down to
 // those of a level that fills the whole table, within the caller's workspace.
+static double env_or(const char* name, double dflt) {
+  const char* v = std::getenv(name);
+  return v != nullptr ? std::atof(v) : dflt;
+}
+
 static int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
+  // tunables (defaults chosen on B200 with tools/sweep): replicas ~ scale * table_rows / vertices,
+  // at most cap_mb per level; levels that already fill the table get `hashed` replicas of the hashed table itself
+  static const double scale = env_or("NRB_BWD_SCALE", 1.0), cap_mb = env_or("NRB_BWD_CAP_MB", 8.0);
+  static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 1.0));
+  static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 3.0));
   const int F = grid->features_per_level;
-  const double table_rows = static_cast<double>(int64_t{1} << grid->log2_hashmap_size);
+  const int64_t T = int64_t{1} << grid->log2_hashmap_size;
+  const double table_rows = static_cast<double>(T);
   int64_t floats = 0;
+  int hashed_used = 0;
   for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
     plan->copies[l] = 0;
     plan->offset[l] = 0;
@@ -279,15 +306,28 @@ static int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
     if (l >= grid->num_levels || M < (int64_t{1} << 16)) continue;
     const int64_t r1 = static_cast<int64_t>(grid->scalings[l]) + 1;
     const double verts = static_cast<double>(r1) * r1 * r1;
-    if (verts * 1.5 > table_rows || r1 > 1024) continue;  // the level already spreads over (most of) the table
-    int copies = static_cast<int>(table_rows / verts + 0.5);
-    copies = std::min(copies, 128);
-    while (copies > 1 && static_cast<double>(copies) * verts * F * 4 > 8.0 * 1024 * 1024) --copies;
-    if (copies <= 1) continue;
+    int copies;
+    int64_t per_copy;
+    if (verts * 1.5 > table_rows || r1 > 1024) {  // the level already spreads over (most of) the table
+      if (hashed <= 1 || hashed_used >= hashed_levels) continue;
+      ++hashed_used;
+      copies = hashed;
+      per_copy = T * F;
+      plan->r1[l] = 0;  // replicas of the hashed level table
+    } else {
+      copies = static_cast<int>(scale * table_rows / verts + 0.5);
+      copies = std::min(copies, 1024);
+      per_copy = r1 * r1 * r1 * F;
+      plan->r1[l] = static_cast<int>(r1);
+    }
+    while (copies > 1 && static_cast<double>(copies) * per_copy * 4 > cap_mb * 1024 * 1024) --copies;
+    if (copies <= 1) {
+      plan->r1[l] = 0;
+      continue;
+    }
     plan->copies[l] = copies;
-    plan->r1[l] = static_cast<int>(r1);
     plan->offset[l] = floats;
-    floats += static_cast<int64_t>(copies) * r1 * r1 * r1 * F;
+    floats += static_cast<int64_t>(copies) * per_copy;
     floats = (floats + 3) & ~int64_t{3};
   }
   return floats * 4;
@@ -311,7 +351,9 @@ static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float
     cudaError_t e = cudaMemsetAsync(workspace, 0, static_cast<size_t>(need), s);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: memset failed: %s", cudaGetErrorString(e));
     for (int l = 0; l < grid->num_levels; ++l)
-      if (plan.copies[l] > 1) vertices += static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l];
+      if (plan.copies[l] > 1)
+        vertices += plan.r1[l] > 0 ? static_cast<int64_t>(plan.r1[l]) * plan.r1[l] * plan.r1[l]
+                                   : (int64_t{1} << grid->log2_hashmap_size);
   } else {  // no (or too small a) workspace: every level scatters straight into the table
     plan.scratch = nullptr;
     for (int l = 0; l < NRB_MAX_LEVELS; ++l) plan.copies[l] = 0;
