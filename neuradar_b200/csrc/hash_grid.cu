@@ -89,8 +89,9 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ base, uint32_t r
 // Coarse levels are therefore accumulated into `copies[l]` replicas of the level's dense vertex lattice
 // ((res+1)^3 x F floats, a few MB in total, L2 resident); warps are dealt round-robin over the replicas, which
 // divides the per-address contention by the replica count, and a small fold kernel adds the replicas into the
-// hashed rows.  Replica counts are chosen so that every level sees about the same number of reductions per address
-// as the finest one.  Shared-memory privatisation was measured and rejected: fp32 shared atomics are CAS loops
+// hashed rows.  Levels that already fill the table but whose samples are still spatially coherent (res 84..256 at
+// T = 2^19) get a few replicas of the hashed level table itself.  Replica counts were swept on B200 (tools_bwd_sweep.py,
+// config 2): 8.5 ms without replicas, 3.9 ms with lattice replicas only, 2.7-2.8 ms with the defaults below.  Shared-memory privatisation was measured and rejected: fp32 shared atomics are CAS loops
 // (ATOMS.CAST.SPIN) on sm_100 and cost ~1 ms per level.
 struct BwdPlan {
   float* scratch;                   // replicated lattices, zeroed by the launcher
@@ -291,9 +292,9 @@ static double env_or(const char* name, double dflt) {
 static int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
   // tunables (defaults chosen on B200 with tools/sweep): replicas ~ scale * table_rows / vertices,
   // at most cap_mb per level; levels that already fill the table get `hashed` replicas of the hashed table itself
-  static const double scale = env_or("NRB_BWD_SCALE", 1.0), cap_mb = env_or("NRB_BWD_CAP_MB", 8.0);
-  static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 1.0));
-  static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 3.0));
+  static const double scale = env_or("NRB_BWD_SCALE", 4.0), cap_mb = env_or("NRB_BWD_CAP_MB", 32.0);
+  static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 4.0));
+  static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 6.0));
   const int F = grid->features_per_level;
   const int64_t T = int64_t{1} << grid->log2_hashmap_size;
   const double table_rows = static_cast<double>(T);
