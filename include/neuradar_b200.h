@@ -136,13 +136,18 @@ typedef struct {
   const float* beta;
   float beta_min;
 } nrb_field_mlp_t;
-/* Activations the backward pass needs, each [M,32] row-major; pass NULL (or NULL members) for inference. */
+/* Activations the backward pass needs.  Feature-major: element (feature j, sample m) at [j * ld + m], with
+ * ld = nrb_field_saved_ld(M) (M rounded up to the 128-sample tile); masks [3][ld] hold one bit per ReLU unit of
+ * h1 / g1 / g2.  Pass NULL (or h1 == NULL) for inference. */
 typedef struct {
   float* h1;
   float* emb;
   float* g1;
   float* g2;
+  uint32_t* masks;
+  int64_t ld;
 } nrb_field_saved_t;
+int64_t nrb_field_saved_ld(int64_t M);
 int nrb_field_mlp_fwd(const nrb_field_mlp_t* mlp, const float* x, const float* sh, int32_t samples_per_ray, int64_t M,
                       float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved, nrb_stream_t stream);
 /* Backward of nrb_field_mlp_fwd.  Inputs: the forward input x, the saved activations, sh, the forward outputs sdf and
@@ -151,10 +156,7 @@ int nrb_field_mlp_fwd(const nrb_field_mlp_t* mlp, const float* x, const float* s
  * / dbiases[i] shaped like the parameters (each optional) and dbeta [1] = d loss / d(|beta| + beta_min). */
 typedef struct {
   const float* x;
-  const float* h1;
-  const float* emb;
-  const float* g1;
-  const float* g2;
+  nrb_field_saved_t saved;
   const float* sh;
   const float* sdf;
   const float* alpha;

@@ -78,11 +78,14 @@ class FieldMlp(C.Structure):
 
 
 class FieldSaved(C.Structure):
-    _fields_ = [("h1", C.c_void_p), ("emb", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p)]
+    _fields_ = [("h1", C.c_void_p), ("emb", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p), ("masks", C.c_void_p),
+                ("ld", C.c_int64)]
 
 
 class FieldBwdIn(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in ("x", "h1", "emb", "g1", "g2", "sh", "sdf", "alpha", "dfeature", "dsdf", "dalpha")]
+    _fields_ = [("x", C.c_void_p), ("saved", FieldSaved)] + [
+        (n, C.c_void_p) for n in ("sh", "sdf", "alpha", "dfeature", "dsdf", "dalpha")
+    ]
 
 
 class FieldBwdOut(C.Structure):
@@ -113,6 +116,7 @@ SIGNATURES = {
     "nrb_sh16": [_P, _P, _I64, _I32, _P],
     "nrb_field_mlp_fwd": [C.POINTER(FieldMlp), _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(FieldSaved), _P],
     "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],
+    "nrb_field_saved_ld": [_I64],
     "nrb_field_mlp_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldBwdIn), C.POINTER(FieldBwdOut), _I32, _I64, _P],
     "nrb_tc_probe": [_P, _P, C.POINTER(C.c_int32), _P, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
@@ -126,7 +130,7 @@ SIGNATURES = {
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
     "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P],
 }
-_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64}
+_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64, "nrb_field_saved_ld": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

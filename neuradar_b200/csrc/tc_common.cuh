@@ -207,15 +207,21 @@ __device__ __forceinline__ void issue_gemm(uint32_t d_tmem, int m, int n, uint32
                                            uint32_t b_hi, uint32_t b_lo, int b_cols, int k_red, bool accumulate_first) {
   const uint32_t idesc = make_idesc_m(m, n, 0, 0);
   const uint32_t a_sbo = static_cast<uint32_t>(a_cols / 4) * 128u, b_sbo = static_cast<uint32_t>(b_cols / 4) * 128u;
+  // the start-address field holds (address >> 4) in the low 14 bits: one k-step (8 tf32 = 256 bytes) adds 16
+  uint64_t ah = make_desc(a_hi, 128, a_sbo), al = make_desc(a_lo, 128, a_sbo);
+  uint64_t bh = make_desc(b_hi, 128, b_sbo), bl = make_desc(b_lo, 128, b_sbo);
   bool acc = accumulate_first;
-  for (int k = 0; k < k_red / 8; ++k) {
-    const uint32_t koff = static_cast<uint32_t>(k) * 256u;
-    const uint64_t ah = make_desc(a_hi + koff, 128, a_sbo), al = make_desc(a_lo + koff, 128, a_sbo);
-    const uint64_t bh = make_desc(b_hi + koff, 128, b_sbo), bl = make_desc(b_lo + koff, 128, b_sbo);
-    mma_tf32(d_tmem, al, bh, idesc, acc);
+  const int steps = k_red / 8;
+#pragma unroll 4
+  for (int k = 0; k < steps; ++k) {
+    mma_tf32(d_tmem, al, bh, idesc, acc);  // small terms first
     mma_tf32(d_tmem, ah, bl, idesc, true);
     mma_tf32(d_tmem, ah, bh, idesc, true);
     acc = true;
+    ah += 16;
+    al += 16;
+    bh += 16;
+    bl += 16;
   }
 }
 
@@ -259,6 +265,53 @@ __device__ __forceinline__ void transpose_tile(const char* src_a, const char* sr
     const uint32_t doff = tile_offset(j, c4, kRows);
     *reinterpret_cast<float4*>(dst_hi + doff) = h;
     *reinterpret_cast<float4*>(dst_lo + doff) = l;
+  }
+}
+
+// Transposed staging straight from registers: thread t = 32*warp + lane holds v[0..31] = row t of a [128 x 32] matrix;
+// the routine writes the TRANSPOSE as a canonical [32 rows x 128 cols] tile (hi / lo halves).  Each group of 4
+// adjacent lanes transposes 4x4 blocks with two shuffle rounds, so that a lane ends up with 4 consecutive samples of
+// one feature = one 16-byte chunk of the destination.  row_offset shifts the destination rows (for [emb | sh] etc).
+template <int kGroups = 8>
+__device__ __forceinline__ void store_rows_transposed_split(char* hi_tile, char* lo_tile, int warp, int lane,
+                                                            const float (&v)[32], int row_offset = 0) {
+  const int i = lane & 3;
+  const int c4 = warp * 8 + (lane >> 2);  // 4-sample chunk index of this lane group
+#pragma unroll
+  for (int g = 0; g < kGroups; ++g) {  // kGroups * 4 destination rows
+    float a0 = v[4 * g], a1 = v[4 * g + 1], a2 = v[4 * g + 2], a3 = v[4 * g + 3];
+    // round 1 (xor 1): swap the off-diagonal elements of each 2x2 block
+    {
+      const bool odd = (i & 1) != 0;
+      const float s01 = odd ? a0 : a1, s23 = odd ? a2 : a3;
+      const float r01 = __shfl_xor_sync(kFull, s01, 1), r23 = __shfl_xor_sync(kFull, s23, 1);
+      if (odd) {
+        a0 = r01;
+        a2 = r23;
+      } else {
+        a1 = r01;
+        a3 = r23;
+      }
+    }
+    // round 2 (xor 2): swap the off-diagonal 2x2 blocks
+    {
+      const bool up = (i & 2) != 0;
+      const float s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+      const float r0 = __shfl_xor_sync(kFull, s0, 2), r1 = __shfl_xor_sync(kFull, s1, 2);
+      if (up) {
+        a0 = r0;
+        a1 = r1;
+      } else {
+        a2 = r0;
+        a3 = r1;
+      }
+    }
+    // this lane now holds feature 4g+i of samples 4*c4 .. 4*c4+3
+    float4 h = make_float4(tf32_hi(a0), tf32_hi(a1), tf32_hi(a2), tf32_hi(a3));
+    float4 l = make_float4(a0 - h.x, a1 - h.y, a2 - h.z, a3 - h.w);
+    const uint32_t off = tile_offset(row_offset + 4 * g + i, c4, kRows);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
   }
 }
 

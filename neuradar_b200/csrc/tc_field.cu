@@ -7,7 +7,10 @@
 // One CTA = 128 threads = one 128-sample tile at a time (persistent over tiles); thread t owns row t: it stages its
 // row of the next layer's A operand (hi/lo tf32 halves) in shared memory, one elected thread issues the layer's
 // tcgen05.mma chain, and every thread reads its accumulator row back with tcgen05.ld for bias + ReLU.  Weights are
-// staged once per CTA.  Two CTAs per SM overlap one tile's MMA/TMEM latency with the other's epilogue.
+// staged once per CTA.  Activations needed by the backward pass are written feature-major ([32][ld], coalesced
+// 128-byte warp stores) together with one bit mask per ReLU layer.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace nrb {
@@ -21,11 +24,13 @@ struct FieldParams {
   float beta_min;
 };
 
-struct FieldSaved {  // activations kept for the backward pass (all optional), row-major
-  float* h1;   // [M,32] post-ReLU hidden of mlp_geo
-  float* emb;  // [M,32] geometry embedding (pre-activation output columns 1..32 of mlp_geo)
-  float* g1;   // [M,32] post-ReLU hidden 1 of mlp_feature
-  float* g2;   // [M,32] post-ReLU hidden 2 of mlp_feature
+struct FieldSaved {  // activations kept for the backward pass, feature-major with leading dimension ld
+  float* h1;         // [32][ld] post-ReLU hidden of mlp_geo
+  float* emb;        // [32][ld] geometry embedding
+  float* g1;         // [32][ld] post-ReLU hidden 1 of mlp_feature
+  float* g2;         // [32][ld] post-ReLU hidden 2 of mlp_feature
+  uint32_t* masks;   // [3][ld] bit j = (unit j > 0) for h1, g1, g2
+  int64_t ld;        // multiple of 128, >= M
 };
 
 constexpr int kTmemCols = 64;
@@ -44,8 +49,6 @@ __host__ __device__ constexpr int field_w_hi(int l) {
 __host__ __device__ constexpr int field_w_lo(int l) { return field_w_hi(l) + field_w_floats(l) * 4; }
 
 struct FieldSmem {
-  __host__ __device__ static constexpr int w_hi(int l) { return field_w_hi(l); }
-  __host__ __device__ static constexpr int w_lo(int l) { return field_w_lo(l); }
   static constexpr int bias = field_w_hi(5);        // 5 x 48 floats
   static constexpr int a_hi = bias + 5 * 48 * 4;    // 128 x 48 floats
   static constexpr int a_lo = a_hi + kRows * 48 * 4;
@@ -71,6 +74,22 @@ __device__ __forceinline__ void store_row32(float* __restrict__ p, const float (
     reinterpret_cast<float4*>(p)[c] = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
 }
 
+// coalesced feature-major store of one row: element j goes to p[j * ld + row]
+__device__ __forceinline__ void store_col32(float* __restrict__ p, int64_t ld, int64_t row, const float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) p[j * ld + row] = v[j];
+}
+
+__device__ __forceinline__ uint32_t relu_bias_mask(float (&v)[32], const float* __restrict__ bias) {
+  uint32_t m = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = fmaxf(v[j] + bias[j], 0.0f);
+    m |= (v[j] > 0.0f ? 1u : 0u) << j;
+  }
+  return m;
+}
+
 __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_constant__ FieldParams prm,
                                                                  const __grid_constant__ FieldSaved sv,
                                                                  const float* __restrict__ x,   // [M,32]
@@ -88,7 +107,7 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldSmem::tmem);
 
   for (int l = 0; l < 5; ++l) {
-    stage_weight_split(prm.w[l], kOut[l], kN[l], kK[l], smem + FieldSmem::w_hi(l), smem + FieldSmem::w_lo(l));
+    stage_weight_split(prm.w[l], kOut[l], kN[l], kK[l], smem + field_w_hi(l), smem + field_w_lo(l));
     for (int j = t; j < 48; j += kRows) s_bias[l * 48 + j] = (j < kOut[l] && prm.b[l] != nullptr) ? __ldg(prm.b[l] + j) : 0.0f;
   }
   if (warp == 0) tmem_alloc<kTmemCols>(tmem_slot);
@@ -100,17 +119,18 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo);
   const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
+  const bool train = sv.h1 != nullptr;
   uint32_t phase = 0;
 
-  // one layer: operands are staged, every thread has fenced; issue, wait, read the accumulator row
+  // one layer: operands are staged; fence, issue, wait for the accumulator
   auto run_layer = [&](int l) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (t == 0) {
       fence_after_sync();
-      issue_gemm_kmajor(tmem_base, a_hi_u, a_lo_u, smem_u32(smem + FieldSmem::w_hi(l)), smem_u32(smem + FieldSmem::w_lo(l)),
-                        kK[l], kN[l], false);
+      issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
+                 smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase);
@@ -119,19 +139,21 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   };
 
   const int64_t tiles = (M + kRows - 1) / kRows;
+  float v[32];
+  if (static_cast<int64_t>(blockIdx.x) < tiles) load_row32(x + min(static_cast<int64_t>(blockIdx.x) * kRows + t, M - 1) * 32, v);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row = tile * kRows + t;
     const bool ok = row < M;
-    const int64_t rr = ok ? row : (M - 1);  // clamp: out-of-range rows compute on a valid row and are not stored
-    float v[32];
+    const int64_t rr = ok ? row : (M - 1);  // out-of-range rows compute on a valid row; only saved activations are stored
     // ---- mlp_geo layer 0: 32 -> 32, ReLU
-    load_row32(x + rr * 32, v);
     store_row_split<32>(a_hi, a_lo, t, v);
+    float xnext[32];  // prefetch the next tile's input row while this tile is in flight
+    const int64_t ntile = tile + gridDim.x;
+    if (ntile < tiles) load_row32(x + min(ntile * kRows + t, M - 1) * 32, xnext);
     run_layer(0);
     tmem_load_row<32>(tmem_base, warp, 0, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + s_bias[j], 0.0f);
-    if (ok && sv.h1 != nullptr) store_row32(sv.h1 + row * 32, v);
+    const uint32_t m_h1 = relu_bias_mask(v, s_bias);
+    if (train) store_col32(sv.h1, sv.ld, row, v);
     store_row_split<32>(a_hi, a_lo, t, v);
     // ---- mlp_geo layer 1: 32 -> 33 (sdf | embedding), no activation
     run_layer(1);
@@ -141,7 +163,7 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     float emb[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) emb[j] = geo[1 + j] + s_bias[48 + 1 + j];
-    if (ok && sv.emb != nullptr) store_row32(sv.emb + row * 32, emb);
+    if (train) store_col32(sv.emb, sv.ld, row, emb);
     // ---- mlp_feature layer 0: [emb | sh] 48 -> 32, ReLU
     {
       float in48[48];
@@ -160,16 +182,19 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     }
     run_layer(2);
     tmem_load_row<32>(tmem_base, warp, 0, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + s_bias[2 * 48 + j], 0.0f);
-    if (ok && sv.g1 != nullptr) store_row32(sv.g1 + row * 32, v);
+    const uint32_t m_g1 = relu_bias_mask(v, s_bias + 2 * 48);
+    if (train) store_col32(sv.g1, sv.ld, row, v);
     store_row_split<32>(a_hi, a_lo, t, v);
     // ---- mlp_feature layer 1: 32 -> 32, ReLU
     run_layer(3);
     tmem_load_row<32>(tmem_base, warp, 0, v);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j] + s_bias[3 * 48 + j], 0.0f);
-    if (ok && sv.g2 != nullptr) store_row32(sv.g2 + row * 32, v);
+    const uint32_t m_g2 = relu_bias_mask(v, s_bias + 3 * 48);
+    if (train) {
+      store_col32(sv.g2, sv.ld, row, v);
+      sv.masks[row] = m_h1;
+      sv.masks[sv.ld + row] = m_g1;
+      sv.masks[2 * sv.ld + row] = m_g2;
+    }
     store_row_split<32>(a_hi, a_lo, t, v);
     // ---- mlp_feature layer 2: 32 -> 32, no activation; residual with the embedding
     run_layer(4);
@@ -181,6 +206,8 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
       sdf[row] = sdf_v;
       alpha[row] = 1.0f / (1.0f + expf(sdf_v * beta));  // sigmoid(-sdf * beta)
     }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = xnext[j];
   }
   fence_before_sync();
   __syncthreads();
@@ -189,20 +216,26 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------------------------------------------
 // Backward of the fused field MLP.  Per 128-sample tile and per layer (last to first) two GEMM chains are issued on
-// the tensor cores from the SAME shared-memory tiles:
-//     dW_l (+)= delta_l^T * in_l        M = 64 (rows >= out_l ignored), N = in_l, reduction over the 128 samples,
-//                                        accumulated in TMEM across ALL tiles of the CTA and flushed once at the end;
-//     dIn_l  = delta_l * W_l            M = 128, N = in_l, reduction over out_l (W_l read MN-major as staged).
+// the tensor cores:
+//     dIn_l  = delta_l * W_l            M = 128, N = in_l, reduction over out_l; A = delta rows (K-major tile),
+//                                        B = W_l^T staged once per CTA.  On the critical path: committed first.
+//     dW_l (+)= delta_l^T * in_l        M = 64 (rows >= out_l ignored), N = in_l, reduction over the 128 samples;
+//                                        A = delta^T, B = in_l^T, both [features x 128 samples] tiles.  delta^T comes
+//                                        straight from registers through 4x4 shuffle transposes, in_l^T is a coalesced
+//                                        copy of the feature-major activations saved by the forward kernel (prefetched
+//                                        one layer ahead).  Accumulated in TMEM across ALL tiles of the CTA, flushed once.
 // Bias gradients are column sums of delta_l (31-shuffle transpose-reduce per warp) kept in shared memory.
 struct FieldBwdIn {
-  const float* x;     // [M,32] hash features (input of the forward pass)
-  const float* h1;    // saved activations, [M,32] each
+  const float* x;         // [M,32] hash features (row-major, as produced by the hash kernel)
+  const float* h1;        // saved activations, feature-major [32][ld]
   const float* emb;
   const float* g1;
   const float* g2;
-  const float* sh;    // [N_rays,16]
-  const float* sdf;   // [M]
-  const float* alpha; // [M]
+  const uint32_t* masks;  // [3][ld]
+  int64_t ld;
+  const float* sh;        // [N_rays,16]
+  const float* sdf;       // [M]
+  const float* alpha;     // [M]
   const float* dfeature;  // [M,32]
   const float* dsdf;      // [M] or null
   const float* dalpha;    // [M] or null
@@ -222,14 +255,13 @@ struct FieldBwdSmem {
   // transposed weights (hi/lo) share the forward kernel's per-layer sizes: W_l^T is [in_l rows x out_l(pad) cols]
   static constexpr int d_hi = field_w_hi(5);            // delta, [128 x 48] K-major (A of the data-gradient GEMM)
   static constexpr int d_lo = d_hi + kRows * 48 * 4;
-  static constexpr int s_raw = d_lo + kRows * 48 * 4;   // layer input rows, [128 x 48] raw fp32 (transpose source)
-  static constexpr int dt_hi = s_raw + kRows * 48 * 4;  // delta^T, [48 x 128] (A of the weight-gradient GEMM)
+  static constexpr int dt_hi = d_lo + kRows * 48 * 4;   // delta^T, [48(+16 read-only slack) x 128]
   static constexpr int dt_lo = dt_hi + 48 * kRows * 4;
-  static constexpr int at_hi = dt_lo + 48 * kRows * 4;  // input^T, [48 x 128] (B of the weight-gradient GEMM)
+  static constexpr int at_hi = dt_lo + 48 * kRows * 4;  // input^T, [48 x 128]
   static constexpr int at_lo = at_hi + 48 * kRows * 4;
   static constexpr int dbacc = at_lo + 48 * kRows * 4;  // [4 warps][5 layers][48]
-  static constexpr int mbar = dbacc + 4 * 5 * 48 * 4;
-  static constexpr int tmem = mbar + 8;
+  static constexpr int mbar = dbacc + 4 * 5 * 48 * 4;   // two mbarriers
+  static constexpr int tmem = mbar + 16;
   static constexpr int total = tmem + 8;
 };
 
@@ -240,6 +272,33 @@ __device__ __forceinline__ int m64_row_of_lane(int lane128) {
   return i < 16 ? q * 16 + i : -1;
 }
 
+// Feature-major activations -> transposed operand tile.  The [32 x 128] block of one tile is 1024 16-byte chunks
+// (feature j, samples 4c..4c+3); thread t takes chunks e = t, t+128, ...: j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31,
+// so that a quarter warp writes 128 contiguous bytes of shared memory.
+__device__ __forceinline__ void prefetch_act_chunks(const float* __restrict__ fm, int64_t ld, int64_t row0, int t,
+                                                    float4 (&pf)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int e = t + q * kRows;
+    const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+    pf[q] = __ldg(reinterpret_cast<const float4*>(fm + j * ld + row0 + 4 * c));
+  }
+}
+
+__device__ __forceinline__ void commit_act_chunks(char* at_hi, char* at_lo, int t, const float4 (&pf)[8]) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int e = t + q * kRows;
+    const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+    const float4 a = pf[q];
+    const float4 h = make_float4(tf32_hi(a.x), tf32_hi(a.y), tf32_hi(a.z), tf32_hi(a.w));
+    const float4 l = make_float4(a.x - h.x, a.y - h.y, a.z - h.z, a.w - h.w);
+    const uint32_t off = tile_offset(j, c, kRows);
+    *reinterpret_cast<float4*>(at_hi + off) = h;
+    *reinterpret_cast<float4*>(at_lo + off) = l;
+  }
+}
+
 __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_constant__ FieldParams prm,
                                                                  const __grid_constant__ FieldBwdIn in,
                                                                  const __grid_constant__ FieldBwdOut out,
@@ -248,61 +307,75 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   char* d_hi = smem + FieldBwdSmem::d_hi;
   char* d_lo = smem + FieldBwdSmem::d_lo;
-  char* s_raw = smem + FieldBwdSmem::s_raw;
   char* dt_hi = smem + FieldBwdSmem::dt_hi;
   char* dt_lo = smem + FieldBwdSmem::dt_lo;
   char* at_hi = smem + FieldBwdSmem::at_hi;
   char* at_lo = smem + FieldBwdSmem::at_lo;
   float* dbacc = reinterpret_cast<float*>(smem + FieldBwdSmem::dbacc);
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + FieldBwdSmem::mbar);
+  uint64_t* mbar_data = reinterpret_cast<uint64_t*>(smem + FieldBwdSmem::mbar);
+  uint64_t* mbar_dw = mbar_data + 1;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldBwdSmem::tmem);
 
   for (int l = 0; l < 5; ++l)
     stage_weight_transposed_split(prm.w[l], kOut[l], kN[l], kK[l], smem + field_w_hi(l), smem + field_w_lo(l));
   for (int i = t; i < 4 * 5 * 48; i += kRows) dbacc[i] = 0.0f;
   if (warp == 0) tmem_alloc<kBwdTmemCols>(tmem_slot);
-  if (t == 0) mbar_init(mbar, 1);
+  if (t == 0) {
+    mbar_init(mbar_data, 1);
+    mbar_init(mbar_dw, 1);
+  }
   fence_async_smem();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
-  uint32_t phase = 0;
-  bool first = true;
+  uint32_t phase_data = 0, phase_dw = 0;
+  bool first = true, dw_pending = false;
   float dbeta_acc = 0.0f;
   float* my_db = dbacc + warp * 5 * 48;
 
-  // delta rows are in d_hi/d_lo (dcols columns), input rows in s_raw (acols columns): transpose both, then issue
-  //   dW_l (+)= delta^T in   (M = 64, N = acols, reduction over the 128 samples)   -> TMEM column kDwCol[l]
-  //   dIn   = delta W_l      (M = 128, N = acols, reduction over kred delta columns) -> TMEM column 0
-  auto run_layer = [&](int l, int dcols, int acols, int kred) {
-    __syncthreads();
-    transpose_tile<false>(d_hi, d_lo, dcols, dt_hi, dt_lo);
-    transpose_tile<true>(s_raw, nullptr, acols, at_hi, at_lo);
+  // Tiles are staged (delta rows in d_*, delta^T in dt_*, input^T in at_*).  Issue both chains; the data chain is
+  // committed first so that the next layer's delta does not wait for the (4x longer) weight-gradient chain.
+  auto issue_layer = [&](int l, int dcols, int acols, int kred) {
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (t == 0) {
       fence_after_sync();
-      issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
-                 smem_u32(at_lo), kRows, kRows, !first);
       issue_gemm(tmem_base, 128, acols, smem_u32(d_hi), smem_u32(d_lo), dcols, smem_u32(smem + field_w_hi(l)),
                  smem_u32(smem + field_w_lo(l)), kN[l], kred, false);
-      mma_commit(mbar);
+      mma_commit(mbar_data);
+      issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
+                 smem_u32(at_lo), kRows, kRows, !first);
+      mma_commit(mbar_dw);
     }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
+    dw_pending = true;
+  };
+  auto wait_data = [&]() {
+    mbar_wait(mbar_data, phase_data);
+    phase_data ^= 1;
     fence_after_sync();
+  };
+  auto wait_dw = [&]() {  // the previous weight-gradient chain still reads dt_* / at_*
+    if (dw_pending) {
+      mbar_wait(mbar_dw, phase_dw);
+      phase_dw ^= 1;
+      dw_pending = false;
+    }
   };
 
   const int64_t tiles = (M + kRows - 1) / kRows;
+  float4 pf[8];
+  if (static_cast<int64_t>(blockIdx.x) < tiles) prefetch_act_chunks(in.g2, in.ld, static_cast<int64_t>(blockIdx.x) * kRows, t, pf);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-    const int64_t row = tile * kRows + t;
+    const int64_t row0 = tile * kRows;
+    const int64_t row = row0 + t;
     const bool ok = row < M;
     const int64_t rr = ok ? row : (M - 1);
-    float delta[32], act[32], tmp[32];
-    // ---- layer 4 (mlp_feature.layers.2): delta = d feature
+    const uint32_t m_h1 = __ldg(in.masks + row), m_g1 = __ldg(in.masks + in.ld + row), m_g2 = __ldg(in.masks + 2 * in.ld + row);
+    float delta[32], tmp[32];
+    // ---- layer 4 (mlp_feature.layers.2): delta = d feature, input g2
     load_row32(in.dfeature + rr * 32, delta);
     if (!ok) {
 #pragma unroll
@@ -311,56 +384,69 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     float demb[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) demb[j] = delta[j];  // residual branch
-    load_row32(in.g2 + rr * 32, act);
+    wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_raw<32>(s_raw, t, act);
+    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    commit_act_chunks(at_hi, at_lo, t, pf);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[4 * 48 + lane] += warp_column_sums(tmp, lane);
-    run_layer(4, 32, 32, 32);
+    issue_layer(4, 32, 32, 32);
+    prefetch_act_chunks(in.g1, in.ld, row0, t, pf);
+    wait_data();
     tmem_load_row<32>(tmem_base, warp, 0, delta);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
-    // ---- layer 3 (mlp_feature.layers.1)
-    load_row32(in.g1 + rr * 32, act);
+    for (int j = 0; j < 32; ++j) delta[j] = ((m_g2 >> j) & 1u) ? delta[j] : 0.0f;
+    // ---- layer 3 (mlp_feature.layers.1): input g1
+    wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_raw<32>(s_raw, t, act);
+    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    commit_act_chunks(at_hi, at_lo, t, pf);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[3 * 48 + lane] += warp_column_sums(tmp, lane);
-    run_layer(3, 32, 32, 32);
+    issue_layer(3, 32, 32, 32);
+    prefetch_act_chunks(in.emb, in.ld, row0, t, pf);
+    wait_data();
     tmem_load_row<32>(tmem_base, warp, 0, delta);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
+    for (int j = 0; j < 32; ++j) delta[j] = ((m_g1 >> j) & 1u) ? delta[j] : 0.0f;
     // ---- layer 2 (mlp_feature.layers.0): input [emb | sh]
-    {
-      float in48[48];
-      load_row32(in.emb + rr * 32, act);
+    wait_dw();
+    store_row_split<32>(d_hi, d_lo, t, delta);
+    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    commit_act_chunks(at_hi, at_lo, t, pf);
+    {  // rows 32..47 of the input^T tile: the ray's SH basis, 16 x 32 chunks, 4 per thread
 #pragma unroll
-      for (int j = 0; j < 32; ++j) in48[j] = act[j];
-      const float4* shp = reinterpret_cast<const float4*>(in.sh + (rr / samples_per_ray) * 16);
+      for (int q = 0; q < 4; ++q) {
+        const int e = t + q * kRows;
+        const int k = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        float a[4];
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 q = __ldg(shp + c);
-        in48[32 + 4 * c] = q.x;
-        in48[32 + 4 * c + 1] = q.y;
-        in48[32 + 4 * c + 2] = q.z;
-        in48[32 + 4 * c + 3] = q.w;
+        for (int i = 0; i < 4; ++i) {
+          const int64_t r = min(row0 + 4 * c + i, M - 1);
+          a[i] = __ldg(in.sh + (r / samples_per_ray) * 16 + k);
+        }
+        const float4 h = make_float4(tf32_hi(a[0]), tf32_hi(a[1]), tf32_hi(a[2]), tf32_hi(a[3]));
+        const float4 l = make_float4(a[0] - h.x, a[1] - h.y, a[2] - h.z, a[3] - h.w);
+        const uint32_t off = tile_offset(32 + k, c, kRows);
+        *reinterpret_cast<float4*>(at_hi + off) = h;
+        *reinterpret_cast<float4*>(at_lo + off) = l;
       }
-      store_row_split<32>(d_hi, d_lo, t, delta);
-      store_row_raw<48>(s_raw, t, in48);
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[2 * 48 + lane] += warp_column_sums(tmp, lane);
-    run_layer(2, 32, 48, 32);
+    issue_layer(2, 32, 48, 32);
+    prefetch_act_chunks(in.h1, in.ld, row0, t, pf);
+    wait_data();
     {
       float din[48];
       tmem_load_row<48>(tmem_base, warp, 0, din);
 #pragma unroll
       for (int j = 0; j < 32; ++j) demb[j] += din[j];  // the SH part of the input carries no gradient
     }
-    // ---- layer 1 (mlp_geo.layers.1): delta = [d sdf | d emb], padded to 48 columns
+    // ---- layer 1 (mlp_geo.layers.1): delta = [d sdf | d emb], padded to 48 columns; input h1
     float dsdf_v = 0.0f;
     if (ok) {
       const float a = __ldg(in.alpha + row), sd = __ldg(in.sdf + row);
@@ -369,6 +455,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       dsdf_v = (in.dsdf != nullptr ? __ldg(in.dsdf + row) : 0.0f) - da * beta * s;
       dbeta_acc -= da * sd * s;
     }
+    wait_dw();
     {
       float d48[48];
       d48[0] = dsdf_v;
@@ -376,10 +463,19 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       for (int j = 0; j < 32; ++j) d48[1 + j] = demb[j];
 #pragma unroll
       for (int j = 33; j < 48; ++j) d48[j] = 0.0f;
-      load_row32(in.h1 + rr * 32, act);
       store_row_split<48>(d_hi, d_lo, t, d48);
-      store_row_raw<32>(s_raw, t, act);
+      // delta^T rows 0..31 = [dsdf, demb[0..30]], rows 32..47 = [demb[31], 0, ...]
+      float lo32[32], hi16[32];
+      lo32[0] = dsdf_v;
+#pragma unroll
+      for (int j = 1; j < 32; ++j) lo32[j] = demb[j - 1];
+      hi16[0] = demb[31];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) hi16[j] = 0.0f;
+      store_rows_transposed_split(dt_hi, dt_lo, warp, lane, lo32);
+      store_rows_transposed_split<4>(dt_hi, dt_lo, warp, lane, hi16, 32);  // rows 32..47 only
     }
+    commit_act_chunks(at_hi, at_lo, t, pf);
     {
       const float s0 = warp_sum(dsdf_v);
       if (lane == 0) my_db[1 * 48 + 0] += s0;
@@ -387,18 +483,27 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       for (int j = 0; j < 32; ++j) tmp[j] = demb[j];
       my_db[1 * 48 + 1 + lane] += warp_column_sums(tmp, lane);
     }
-    run_layer(1, 48, 32, 40);
+    issue_layer(1, 48, 32, 40);
+    float xrow[32];
+    load_row32(in.x + rr * 32, xrow);
+    wait_data();
     tmem_load_row<32>(tmem_base, warp, 0, delta);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) delta[j] = act[j] > 0.0f ? delta[j] : 0.0f;
-    // ---- layer 0 (mlp_geo.layers.0)
-    load_row32(in.x + rr * 32, act);
+    for (int j = 0; j < 32; ++j) delta[j] = ((m_h1 >> j) & 1u) ? delta[j] : 0.0f;
+    // ---- layer 0 (mlp_geo.layers.0): input x (row-major in memory: transposed through registers)
+    wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_row_raw<32>(s_raw, t, act);
+    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    store_rows_transposed_split(at_hi, at_lo, warp, lane, xrow);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
     my_db[0 * 48 + lane] += warp_column_sums(tmp, lane);
-    run_layer(0, 32, 32, 32);
+    issue_layer(0, 32, 32, 32);
+    {
+      const int64_t ntile = tile + gridDim.x;
+      if (ntile < tiles) prefetch_act_chunks(in.g2, in.ld, ntile * kRows, t, pf);
+    }
+    wait_data();
     if (out.dx != nullptr) {
       tmem_load_row<32>(tmem_base, warp, 0, delta);
       if (ok) store_row32(out.dx + row * 32, delta);
@@ -406,6 +511,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     first = false;
   }
   // ---- flush: weight gradients from TMEM, bias gradients from shared memory, beta
+  wait_dw();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -566,39 +672,6 @@ extern "C" int nrb_tc_linear(const float* x, const float* w, const float* b, int
   return finish_launch("nrb_tc_linear");
 }
 
-extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const float* sh, int32_t samples_per_ray,
-                                 int64_t M, float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved,
-                                 nrb_stream_t stream) {
-  NRB_REQUIRE(p && x && sh && feature && sdf && alpha && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG,
-              "nrb_field_mlp_fwd: null pointer or bad size");
-  for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_fwd: weights[%d] is null", l);
-  NRB_REQUIRE(p->beta != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_fwd: beta is null");
-  NRB_REQUIRE(aligned16(x) && aligned16(sh) && aligned16(feature), NRB_ERR_ALIGNMENT,
-              "nrb_field_mlp_fwd: x, sh and feature must be 16-byte aligned");
-  if (M == 0) return NRB_OK;
-  FieldParams prm;
-  for (int l = 0; l < 5; ++l) {
-    prm.w[l] = p->weights[l];
-    prm.b[l] = p->biases[l];
-  }
-  prm.beta = p->beta;
-  prm.beta_min = p->beta_min;
-  FieldSaved sv{nullptr, nullptr, nullptr, nullptr};
-  if (saved != nullptr) {
-    sv.h1 = saved->h1;
-    sv.emb = saved->emb;
-    sv.g1 = saved->g1;
-    sv.g2 = saved->g2;
-  }
-  cudaError_t e = cudaFuncSetAttribute(field_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::total);
-  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-  const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
-  field_mlp_fwd_kernel<<<grid, tc::kRows, FieldSmem::total, static_cast<cudaStream_t>(stream)>>>(
-      prm, sv, x, sh, samples_per_ray, M, feature, sdf, alpha);
-  return finish_launch("nrb_field_mlp_fwd");
-}
-
 extern "C" int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11, float* dump, nrb_stream_t stream) {
   NRB_REQUIRE(P && Q && cfg11 && dump, NRB_ERR_BAD_ARG, "nrb_tc_probe: null pointer");
   ProbeCfg c{cfg11[0], cfg11[1], cfg11[2], cfg11[3], cfg11[4], cfg11[5], cfg11[6], cfg11[7], cfg11[8], cfg11[9], cfg11[10]};
@@ -609,17 +682,7 @@ extern "C" int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11
   return finish_launch("nrb_tc_probe");
 }
 
-extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
-                                 int32_t samples_per_ray, int64_t M, nrb_stream_t stream) {
-  NRB_REQUIRE(p && in && out && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: null pointer or bad size");
-  NRB_REQUIRE(in->x && in->h1 && in->emb && in->g1 && in->g2 && in->sh && in->sdf && in->alpha && in->dfeature,
-              NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: a required input is null");
-  for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: weights[%d] is null", l);
-  NRB_REQUIRE(p->beta != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: beta is null");
-  NRB_REQUIRE(aligned16(in->x) && aligned16(in->h1) && aligned16(in->emb) && aligned16(in->g1) && aligned16(in->g2) &&
-                  aligned16(in->sh) && aligned16(in->dfeature) && (out->dx == nullptr || aligned16(out->dx)),
-              NRB_ERR_ALIGNMENT, "nrb_field_mlp_bwd: row-major [M,32] arrays must be 16-byte aligned");
-  if (M == 0) return NRB_OK;
+static FieldParams to_params(const nrb_field_mlp_t* p) {
   FieldParams prm;
   for (int l = 0; l < 5; ++l) {
     prm.w[l] = p->weights[l];
@@ -627,7 +690,55 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   }
   prm.beta = p->beta;
   prm.beta_min = p->beta_min;
-  FieldBwdIn bi{in->x, in->h1, in->emb, in->g1, in->g2, in->sh, in->sdf, in->alpha, in->dfeature, in->dsdf, in->dalpha};
+  return prm;
+}
+
+extern "C" int64_t nrb_field_saved_ld(int64_t M) { return (M + tc::kRows - 1) / tc::kRows * tc::kRows; }
+
+extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const float* sh, int32_t samples_per_ray,
+                                 int64_t M, float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved,
+                                 nrb_stream_t stream) {
+  NRB_REQUIRE(p && x && sh && feature && sdf && alpha && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG,
+              "nrb_field_mlp_fwd: null pointer or bad size");
+  for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_fwd: weights[%d] is null", l);
+  NRB_REQUIRE(p->beta != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_fwd: beta is null");
+  NRB_REQUIRE(aligned16(x) && aligned16(sh) && aligned16(feature), NRB_ERR_ALIGNMENT,
+              "nrb_field_mlp_fwd: x, sh and feature must be 16-byte aligned");
+  if (M == 0) return NRB_OK;
+  FieldSaved sv{nullptr, nullptr, nullptr, nullptr, nullptr, 0};
+  if (saved != nullptr && saved->h1 != nullptr) {
+    NRB_REQUIRE(saved->emb && saved->g1 && saved->g2 && saved->masks, NRB_ERR_BAD_ARG,
+                "nrb_field_mlp_fwd: saved activations must be given together");
+    NRB_REQUIRE(saved->ld >= M && saved->ld % tc::kRows == 0, NRB_ERR_BAD_ARG,
+                "nrb_field_mlp_fwd: saved->ld must be nrb_field_saved_ld(M)");
+    sv = FieldSaved{saved->h1, saved->emb, saved->g1, saved->g2, saved->masks, saved->ld};
+  }
+  cudaError_t e = cudaFuncSetAttribute(field_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::total);
+  NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+  const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
+  field_mlp_fwd_kernel<<<grid, tc::kRows, FieldSmem::total, static_cast<cudaStream_t>(stream)>>>(
+      to_params(p), sv, x, sh, samples_per_ray, M, feature, sdf, alpha);
+  return finish_launch("nrb_field_mlp_fwd");
+}
+
+extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
+                                 int32_t samples_per_ray, int64_t M, nrb_stream_t stream) {
+  NRB_REQUIRE(p && in && out && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: null pointer or bad size");
+  NRB_REQUIRE(in->x && in->saved.h1 && in->saved.emb && in->saved.g1 && in->saved.g2 && in->saved.masks && in->sh &&
+                  in->sdf && in->alpha && in->dfeature,
+              NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: a required input is null");
+  NRB_REQUIRE(in->saved.ld >= M && in->saved.ld % tc::kRows == 0, NRB_ERR_BAD_ARG,
+              "nrb_field_mlp_bwd: saved.ld must be nrb_field_saved_ld(M)");
+  for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: weights[%d] is null", l);
+  NRB_REQUIRE(p->beta != nullptr, NRB_ERR_BAD_ARG, "nrb_field_mlp_bwd: beta is null");
+  NRB_REQUIRE(aligned16(in->x) && aligned16(in->saved.h1) && aligned16(in->saved.emb) && aligned16(in->saved.g1) &&
+                  aligned16(in->saved.g2) && aligned16(in->sh) && aligned16(in->dfeature) &&
+                  (out->dx == nullptr || aligned16(out->dx)),
+              NRB_ERR_ALIGNMENT, "nrb_field_mlp_bwd: arrays must be 16-byte aligned");
+  if (M == 0) return NRB_OK;
+  FieldBwdIn bi{in->x,  in->saved.h1, in->saved.emb, in->saved.g1,  in->saved.g2, in->saved.masks, in->saved.ld,
+                in->sh, in->sdf,      in->alpha,     in->dfeature, in->dsdf,     in->dalpha};
   FieldBwdOut bo;
   bo.dx = out->dx;
   for (int l = 0; l < 5; ++l) {
@@ -639,6 +750,7 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
-  field_mlp_bwd_kernel<<<grid, tc::kRows, FieldBwdSmem::total, static_cast<cudaStream_t>(stream)>>>(prm, bi, bo, samples_per_ray, M);
+  field_mlp_bwd_kernel<<<grid, tc::kRows, FieldBwdSmem::total, static_cast<cudaStream_t>(stream)>>>(
+      to_params(p), bi, bo, samples_per_ray, M);
   return finish_launch("nrb_field_mlp_bwd");
 }

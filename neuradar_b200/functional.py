@@ -294,6 +294,19 @@ def _field_struct(weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]],
     return m
 
 
+def _alloc_field_saved(M: int, dev):
+    """Feature-major activation buffers [32, ld] x 4 and the ReLU bit masks [3, ld] (see nrb_field_saved_t)."""
+    ld = int(_lib_().nrb_field_saved_ld(M))
+    acts = [torch.empty((32, ld), device=dev, dtype=torch.float32) for _ in range(4)]
+    masks = torch.empty((3, ld), device=dev, dtype=torch.int32)
+    return acts + [masks]
+
+
+def _fill_saved(sv, saved) -> None:
+    sv.h1, sv.emb, sv.g1, sv.g2, sv.masks = (ptr(t) for t in saved)
+    sv.ld = saved[0].shape[1]
+
+
 def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Tensor],
                       biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float, save: bool = False):
     """Inference-only entry of the fused tensor-core field MLP: (feature [M,32], sdf [M], alpha [M], saved)."""
@@ -309,8 +322,8 @@ def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequ
     saved = None
     sv = _lib.FieldSaved()
     if save:
-        saved = [torch.empty((M, 32), device=dev, dtype=torch.float32) for _ in range(4)]
-        sv.h1, sv.emb, sv.g1, sv.g2 = (ptr(t) for t in saved)
+        saved = _alloc_field_saved(M, dev)
+        _fill_saved(sv, saved)
     m = _field_struct(weights, biases, beta, beta_min)
     _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
               ptr(alpha), C.byref(sv), stream_ptr())
@@ -344,8 +357,8 @@ class _FieldMlp(torch.autograd.Function):
         sv = _lib.FieldSaved()
         saved = []
         if train:
-            saved = [torch.empty((M, 32), device=dev, dtype=torch.float32) for _ in range(4)]
-            sv.h1, sv.emb, sv.g1, sv.g2 = (ptr(t) for t in saved)
+            saved = _alloc_field_saved(M, dev)
+            _fill_saved(sv, saved)
         m = _field_struct(weights, biases, beta, beta_min)
         _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
                   ptr(alpha), C.byref(sv), stream_ptr())
@@ -359,12 +372,13 @@ class _FieldMlp(torch.autograd.Function):
     @custom_bwd(device_type="cuda")
     def backward(ctx, dfeature, dsdf, dalpha):
         t = ctx.saved_tensors
-        x, sh, beta, sdf, alpha, h1, emb, g1, g2 = t[:9]
-        weights = list(t[9:14])
-        rest = list(t[14:])
+        x, sh, beta, sdf, alpha = t[:5]
+        saved = list(t[5:10])
+        weights = list(t[10:15])
+        rest = list(t[15:])
         biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
         M = x.shape[0]
-        dfeature = torch.zeros_like(h1) if dfeature is None else f32c(dfeature)
+        dfeature = torch.zeros_like(x) if dfeature is None else f32c(dfeature)
         dsdf = None if dsdf is None else f32c(dsdf)
         dalpha = None if dalpha is None else f32c(dalpha)
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
@@ -373,7 +387,8 @@ class _FieldMlp(torch.autograd.Function):
         dbeta_eff = torch.zeros((1,), device=x.device, dtype=torch.float32)
         m = _field_struct(weights, biases, beta, ctx.beta_min)
         bi = _lib.FieldBwdIn()
-        bi.x, bi.h1, bi.emb, bi.g1, bi.g2, bi.sh = ptr(x), ptr(h1), ptr(emb), ptr(g1), ptr(g2), ptr(sh)
+        bi.x, bi.sh = ptr(x), ptr(sh)
+        _fill_saved(bi.saved, saved)
         bi.sdf, bi.alpha, bi.dfeature, bi.dsdf, bi.dalpha = ptr(sdf), ptr(alpha), ptr(dfeature), ptr(dsdf), ptr(dalpha)
         bo = _lib.FieldBwdOut()
         bo.dx = ptr(dx)

@@ -67,7 +67,9 @@ def test_field_mlp_forward(N, S):
     assert rel_err(sdf, rs) <= 1e-5
     assert float((alpha.cpu() - ra).abs().max()) <= 2e-5
     h1 = torch.relu(torch.nn.functional.linear(x, ws[0], bs[0]))
-    assert rel_err(saved[0], h1) <= 1e-5
+    assert rel_err(saved[0][:, : N * S].T, h1) <= 1e-5  # saved activations are feature-major [32, ld]
+    bits = (saved[4][0, : N * S].cpu().to(torch.int64)[:, None] >> torch.arange(32)) & 1
+    assert torch.equal(bits.bool(), saved[0][:, : N * S].T.cpu() > 0)
 
 
 @pytest.mark.parametrize("N,S", [(8, 48), (600, 48), (129, 33)])
