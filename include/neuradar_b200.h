@@ -241,11 +241,11 @@ int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float
                      const nrb_intervals_t* iv, float* density, float* weights, float* saved_feats, float* saved_pre,
                      nrb_stream_t stream);
 /* Backward of the fused round given dweights [N,S] and/or ddensity [N,S] (either may be NULL):
- * dtable += ..., ddecoder_w [L*F] += ... */
+ * dtable += ..., ddecoder_w [L*F] += ...; workspace as for nrb_hash_bwd (nrb_hash_bwd_workspace_bytes(grid, N*S)). */
 int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w, float static_scale,
                      const nrb_intervals_t* iv, const float* saved_feats, const float* saved_pre,
                      const float* dweights, const float* ddensity, float* dtable, float* ddecoder_w,
-                     nrb_stream_t stream);
+                     void* workspace, int64_t workspace_bytes, nrb_stream_t stream);
 
 #ifdef __cplusplus
 }

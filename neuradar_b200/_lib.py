@@ -128,7 +128,7 @@ SIGNATURES = {
     "nrb_accumulate_bwd": [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
     "nrb_alpha_composite_bwd": [_P, _P, C.POINTER(Intervals), _I64, _I32, _F, _I32, _P, _P, _P, _P, _P, _P, _P],
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
-    "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P],
+    "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P, _I64, _P],
 }
 _RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64, "nrb_field_saved_ld": C.c_int64}
 

@@ -4,6 +4,7 @@
 // RaySamples.get_weights (nerfstudio/cameras/rays.py:188-210); trunc_exp backward clamps the exponent to +-15
 // (nerfstudio/field_components/activations.py:28-41).
 #include "common.cuh"
+#include "hash_bwd_plan.cuh"
 
 namespace nrb {
 
@@ -77,7 +78,7 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_fwd_kernel(
 
 template <int F>
 __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
-    const __grid_constant__ PropGrid g, const float* __restrict__ origins, const float* __restrict__ directions,
+    const __grid_constant__ PropGrid g, const __grid_constant__ BwdPlan plan, const float* __restrict__ origins, const float* __restrict__ directions,
     const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
     const float* __restrict__ saved_feats, const float* __restrict__ saved_pre, const float* __restrict__ dweights,
     const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder) {
@@ -169,19 +170,8 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
               }
               float w8[8];
               corner_weights(cell, w8);
-              float* base = dtable + (static_cast<size_t>(l) << g.log2_size) * F;
-#pragma unroll
-              for (int k = 0; k < 8; ++k) {
-                float* p = base + static_cast<size_t>(cell.row[k]) * F;
-                if constexpr (F == 1) {
-                  atomicAdd(p, gr[0] * w8[k]);
-                } else if constexpr (F == 2) {
-                  atomicAdd(reinterpret_cast<float2*>(p), make_float2(gr[0] * w8[k], gr[1] * w8[k]));
-                } else {
-                  atomicAdd(reinterpret_cast<float4*>(p),
-                            make_float4(gr[0] * w8[k], gr[1] * w8[k], gr[2] * w8[k], gr[3] * w8[k]));
-                }
-              }
+              scatter_corners<F>(plan, l, g.log2_size, scal, q.x, q.y, q.z, cell, gr, w8, dtable,
+                                 static_cast<unsigned>(blockIdx.x * kPropWarps + (threadIdx.x >> 5)));
             }
           }
         }
@@ -252,7 +242,7 @@ extern "C" int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
 extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
                                 float static_scale, const nrb_intervals_t* iv, const float* saved_feats,
                                 const float* saved_pre, const float* dweights, const float* ddensity, float* dtable,
-                                float* ddecoder_w, nrb_stream_t stream) {
+                                float* ddecoder_w, void* workspace, int64_t workspace_bytes, nrb_stream_t stream) {
   if (int rc = check_proposal("nrb_proposal_bwd", rays, grid, decoder_w, static_scale, iv)) return rc;
   NRB_REQUIRE(saved_feats && saved_pre && dtable, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: null pointer");
   NRB_REQUIRE(dweights || ddensity, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: no upstream gradient");
@@ -262,8 +252,11 @@ extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
   const PropGrid g = make_prop_grid(grid, decoder_w);
   const unsigned blocks = blocks_for(N, kPropWarps);
   auto s = static_cast<cudaStream_t>(stream);
+  BwdPlan plan;
+  int64_t vertices = 0;
+  if (int rc = prepare_bwd_plan(grid, N * iv->num_samples, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
 #define NRB_LAUNCH(F)                                                                                              \
-  proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, rays->origins, rays->directions, rays->pixel_area,  \
+  proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, plan, rays->origins, rays->directions, rays->pixel_area,  \
                                                             static_scale, *iv, N, saved_feats, saved_pre,          \
                                                             dweights, ddensity, dtable, ddecoder_w)
   switch (grid->features_per_level) {
@@ -272,5 +265,10 @@ extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
     default: NRB_LAUNCH(4); break;
   }
 #undef NRB_LAUNCH
+  switch (grid->features_per_level) {
+    case 1: launch_fold<1>(grid, plan, dtable, vertices, s); break;
+    case 2: launch_fold<2>(grid, plan, dtable, vertices, s); break;
+    default: launch_fold<4>(grid, plan, dtable, vertices, s); break;
+  }
   return finish_launch("nrb_proposal_bwd");
 }

@@ -643,8 +643,10 @@ class _ProposalRound(torch.autograd.Function):
         ddensity = None if ddensity is None else f32c(ddensity)
         dweights = None if dweights is None else f32c(dweights)
         g, r, i = ctx.spec.struct(table), ctx.rays.struct(), ctx.iv.struct()
+        n_pts = ctx.rays.num_rays * ctx.iv.num_samples
+        ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), n_pts)), table.device)
         _lib.call("nrb_proposal_bwd", C.byref(r), C.byref(g), ptr(dec), ctx.scale, C.byref(i), ptr(feats), ptr(pre),
-                                     ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), stream_ptr())
+                  ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, stream_ptr())
         return dtable, ddec.reshape(ctx.dec_shape), None, None, None, None
 
 
