@@ -24,7 +24,7 @@ from .field_components import (
     StaticSettings,
     trunc_exp,
 )
-from .rays import RaySamples
+from .rays import RaySamples, per_ray_of
 
 
 class FieldHeadNames(Enum):
@@ -109,10 +109,10 @@ class NeuRADField(nn.Module):
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
         if compute_normals:
             raise NotImplementedError("normals are not rendered on the NeuRadar path")
-        rays, iv = ray_samples.per_ray()
+        rays, iv = per_ray_of(ray_samples)
         N, S = rays.num_rays, iv.num_samples
         features = self.hashgrid.encode_samples(rays, iv)
-        shape = ray_samples.shape if len(ray_samples.shape) == 2 else (N, S)
+        shape = tuple(ray_samples.shape) if len(ray_samples.shape) == 2 else (N, S)
         if self._tensor_core_path():
             # everything after the hash grid in ONE tcgen05 kernel (and one for its backward)
             sh = self.direction_encoding(get_normalized_directions(rays.directions))
@@ -177,7 +177,7 @@ class NeuRADProposalField(nn.Module):
 
     def density_and_weights(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
         """One kernel for get_density + RaySamples.get_weights: ([N,S,1], [N,S,1])."""
-        rays, iv = ray_samples.per_ray()
+        rays, iv = per_ray_of(ray_samples)
         grid = self.hashgrid.static_grid
         dens, w = F.proposal_round(grid.hash_table, self.density_decoder.weight, rays, iv, grid.spec,
                                    self.hashgrid.static_scale)

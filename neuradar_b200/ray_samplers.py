@@ -15,7 +15,7 @@ import torch
 from torch import Tensor, nn
 
 from . import functional as F
-from .rays import RayBundle, RaySamples
+from .rays import RayBundle, RaySamples, ray_data_of
 
 
 def _make_ray_samples(ray_bundle: RayBundle, rays: F.RayData, sbins: Tensor, ebins: Tensor, spacing, fn) -> RaySamples:
@@ -73,7 +73,7 @@ class PowerSampler(Sampler):
         assert ray_bundle.fars is not None
         num_samples = num_samples or self.num_samples
         assert num_samples is not None
-        rays = ray_bundle.ray_data()
+        rays = ray_data_of(ray_bundle)
         jitter = None
         if self.train_stratified and self.training:
             shape = (rays.num_rays, 1) if self.single_jitter else (rays.num_rays, num_samples + 1)
@@ -111,12 +111,12 @@ class PDFSampler(Sampler):
         assert num_samples is not None
         assert ray_samples.spacing_starts is not None and ray_samples.spacing_ends is not None, \
             "ray_sample spacing_starts and spacing_ends must be provided"
-        if ray_samples.spacing is None:
+        if getattr(ray_samples, "spacing", None) is None:
             raise NotImplementedError("PDFSampler needs ray samples produced by PowerSampler/PDFSampler of this package")
-        rays = ray_samples.ray_data if ray_samples.ray_data is not None else ray_bundle.ray_data()
-        if rays.nears is None or rays.fars is None:
-            rays = ray_bundle.ray_data()
-        sbins_in = ray_samples.spacing_bins
+        rays = getattr(ray_samples, "ray_data", None)
+        if rays is None or rays.nears is None or rays.fars is None:
+            rays = ray_data_of(ray_bundle)
+        sbins_in = getattr(ray_samples, "spacing_bins", None)
         if sbins_in is None:
             sbins_in = torch.cat([ray_samples.spacing_starts[..., 0], ray_samples.spacing_ends[..., -1:, 0]], dim=-1)
         jitter = None

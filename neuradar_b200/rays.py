@@ -22,6 +22,40 @@ from torch import Tensor
 from . import functional as F
 
 
+# ------------------------------------------------------------------------------------------------
+# Duck-typed accessors: the kernels need the un-broadcast per-ray tensors.  These work on this package's containers
+# AND on the reference's own nerfstudio.cameras.rays.{RayBundle,RaySamples,Frustums} (same attribute names), which is
+# what makes the modules drop in under the unmodified NeuRadarModel.
+# ------------------------------------------------------------------------------------------------
+def ray_data_of(ray_bundle) -> F.RayData:
+    """Per-ray tensors of a RayBundle-like object."""
+    return F.RayData(
+        ray_bundle.origins.reshape(-1, 3),
+        ray_bundle.directions.reshape(-1, 3),
+        ray_bundle.pixel_area.reshape(-1),
+        None if ray_bundle.nears is None else ray_bundle.nears.reshape(-1),
+        None if ray_bundle.fars is None else ray_bundle.fars.reshape(-1),
+    )
+
+
+def frustums_per_ray(frustums) -> Tuple[F.RayData, F.SampleIntervals]:
+    """Un-broadcast view of Frustums-like [N rays, S samples] (or of a flat batch: every sample its own ray)."""
+    shape = tuple(frustums.origins.shape[:-1])
+    if len(shape) == 2 and (frustums.origins.stride(1) == 0 or shape[1] == 1):
+        rays = F.RayData(frustums.origins[:, 0, :], frustums.directions[:, 0, :], frustums.pixel_area[:, 0, 0])
+        return rays, F.SampleIntervals(frustums.starts, frustums.ends)
+    rays = F.RayData(frustums.origins.reshape(-1, 3), frustums.directions.reshape(-1, 3), frustums.pixel_area.reshape(-1))
+    return rays, F.SampleIntervals(frustums.starts.reshape(-1, 1), frustums.ends.reshape(-1, 1))
+
+
+def per_ray_of(ray_samples) -> Tuple[F.RayData, F.SampleIntervals]:
+    """(per-ray data, sample intervals) of a RaySamples-like object; uses what this package's samplers attached."""
+    rd = getattr(ray_samples, "ray_data", None)
+    if rd is not None and ray_samples.frustums.starts.dim() == 3:
+        return rd, F.SampleIntervals(ray_samples.frustums.starts, ray_samples.frustums.ends)
+    return frustums_per_ray(ray_samples.frustums)
+
+
 @dataclass
 class GaussiansStd:
     """Isotropic gaussians: mean [*batch, dim], std [*batch, 1] (utils/math.py:114-145)."""
@@ -156,12 +190,7 @@ class Frustums(TensorDataclass):
 
     def _per_ray(self) -> Tuple[F.RayData, F.SampleIntervals]:
         """Un-broadcast view of these frustums for the kernels: [N rays, S samples]."""
-        if len(self.shape) == 2 and (self.origins.stride(1) == 0 or self.shape[1] == 1):
-            rays = F.RayData(self.origins[:, 0, :], self.directions[:, 0, :], self.pixel_area[:, 0, 0])
-            return rays, F.SampleIntervals(self.starts, self.ends)
-        flat = self.flatten()  # every sample is its own ray
-        rays = F.RayData(flat.origins, flat.directions, flat.pixel_area[:, 0])
-        return rays, F.SampleIntervals(flat.starts.reshape(-1, 1), flat.ends.reshape(-1, 1))
+        return frustums_per_ray(self)
 
     def get_fast_isotropic_gaussian(self, num_multisamples: int = 1, contraction_scale: Optional[float] = None) -> GaussiansStd:
         """Gaussian approximation of each frustum (cameras/rays.py:109-124), one multisample.
@@ -212,9 +241,7 @@ class RaySamples(TensorDataclass):
         return F.SampleIntervals(self.frustums.starts, self.frustums.ends)
 
     def per_ray(self) -> Tuple[F.RayData, F.SampleIntervals]:
-        if self.ray_data is not None and len(self.shape) == 2:
-            return self.ray_data, self.intervals()
-        return self.frustums._per_ray()
+        return per_ray_of(self)
 
     def get_weights(self, densities: Tensor) -> Tensor:
         """Weights from densities [*, S, 1] (cameras/rays.py:188-210), one warp-scan kernel."""
@@ -267,9 +294,7 @@ class RayBundle(TensorDataclass):
         return self.flatten()[start_idx:end_idx]
 
     def ray_data(self) -> F.RayData:
-        return F.RayData(self.origins.reshape(-1, 3), self.directions.reshape(-1, 3), self.pixel_area.reshape(-1),
-                         None if self.nears is None else self.nears.reshape(-1),
-                         None if self.fars is None else self.fars.reshape(-1))
+        return ray_data_of(self)
 
     def get_ray_samples(
         self,
