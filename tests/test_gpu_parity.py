@@ -473,3 +473,65 @@ def test_full_size_properties(nb):
         else:
             assert p.grad is not None and bool(torch.isfinite(p.grad).all()), name
     assert float(model.field.hashgrid.static_grid.hash_table.grad.abs().sum()) > 0
+
+
+# ------------------------------------------------------------------------------------------------ other BASELINE configs
+def test_config4_large_scene_shapes_vs_oracle(nb):
+    """BASELINE config 4 without actors at reduced table size: main grid L8/F4 (res 32..8191), 128 samples per ray,
+    proposals (128, 64).  Exercises F=4 gathers/reductions, 4-chunk warp scans and the 8191 top level."""
+    S0, S1, S2 = 128, 64, 128
+    model = build_hot_path(log2_main=15, log2_prop=14, num_proposal_samples=(S0, S1), num_nerf_samples=S2, main_levels=8,
+                           main_features=4, main_res=(32, 8192), table_gain=(300.0, 2000.0), seed=5, device=DEV)
+    assert model.field.hashgrid.static_grid.scalings[-1].item() == 8191.0
+    model.train()
+    N = 300
+    rays = synthetic_rays(N, seed=13)
+    g = torch.Generator().manual_seed(14)
+    jit = [torch.rand((N, S0 + 1), generator=g), torch.rand((N, 1), generator=g), torch.rand((N, 1), generator=g)]
+    fld, props = oracle_params(model)
+    with FixedJitter(jit):
+        out = model(make_ray_bundle(rays, DEV))
+    cfg = O.PathConfig(num_proposal_samples=(S0, S1), num_nerf_samples=S2)
+    ref = O.nff_forward(fld, [props[-1], props[-1]], rays["origins"], rays["directions"], scaled_pixel_area(rays),
+                        rays["nears"], rays["fars"], cfg, jit, composite_eps=0.0)
+    assert rel_err(out["features"], ref.features) <= 1e-3
+    assert rel_err(out["depth"], ref.depth) <= 1e-3
+    assert rel_err(out["accumulation"], ref.accumulation) <= 1e-3
+    for i in range(3):
+        assert rel_err(out["weights_list"][i], ref.weights_list[i]) <= 1e-3
+    nb.bench_loss(out).backward()
+    O.bench_loss(ref).backward()
+    assert rel_err(model.field.hashgrid.static_grid.hash_table.grad, fld.grid.table.grad) <= 1e-3
+    assert rel_err(model.field.mlp_geo.layers[0].weight.grad, fld.geo_w[0].grad) <= 1e-3
+    assert rel_err(model.proposal_fields[1].hashgrid.static_grid.hash_table.grad, props[1].grid.table.grad) <= 1e-3
+
+
+def test_config5_inference_sweep(nb):
+    """BASELINE config 5: radar point-cloud render sweep, eval mode (deterministic u), forward only, chunks of 32768
+    rays (eval_num_rays_per_chunk, configs/method_configs.py:380).  One chunk is compared with the oracle on a slice;
+    the sweep itself checks size-independent invariants and chunking invariance."""
+    model = build_hot_path(log2_main=16, log2_prop=16, table_gain=(300.0, 2000.0), seed=6, device=DEV)
+    model.eval()
+    rays = synthetic_rays(4 * 32768, seed=21, mix="radar")
+    depth, acc = [], []
+    with torch.no_grad():
+        for lo in range(0, 4 * 32768, 32768):
+            chunk = {k: v[lo : lo + 32768] for k, v in rays.items()}
+            out = model(make_ray_bundle(chunk, DEV))
+            depth.append(out["depth"])
+            acc.append(out["accumulation"])
+        whole = model(make_ray_bundle({k: v[:65536] for k, v in rays.items()}, DEV))
+    depth, acc = torch.cat(depth), torch.cat(acc)
+    assert bool(torch.isfinite(depth).all()) and float(acc.min()) >= 0 and float(acc.max()) <= 1 + 1e-5
+    assert torch.equal(whole["depth"], depth[:65536]), "eval mode is deterministic: chunking must not change a bit"
+    # radar point head (models/neuradar.py:1025-1029) on the rendered depth vs the oracle, on a 512-ray slice
+    sl = {k: v[:512] for k, v in rays.items()}
+    fld, props = oracle_params(model)
+    ref = O.nff_forward(fld, [props[-1], props[-1]], sl["origins"], sl["directions"], scaled_pixel_area(sl), sl["nears"],
+                        sl["fars"], O.PathConfig(num_proposal_samples=(64, 48), num_nerf_samples=48), None)
+    assert rel_err(depth[:512], ref.depth) <= 1e-3
+    d = sl["directions"]
+    theta, phi = torch.asin(d[:, 2:3]), torch.atan2(d[:, 1:2], d[:, 0:1])
+    pts = O.radar_points(depth[:512].cpu(), theta, phi)
+    assert rel_err(pts, O.radar_points(ref.depth, theta, phi)) <= 1e-3
+    assert rel_err(pts, d * depth[:512].cpu()) <= 1e-5  # unit directions: the point head is direction * depth
