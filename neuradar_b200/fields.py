@@ -106,28 +106,63 @@ class NeuRADField(nn.Module):
             and (c.geo_hidden_dim, c.geo_num_layers, c.nff_hidden_dim, c.nff_num_layers, c.nff_out_dim) == (32, 2, 32, 3, 32)
         )
 
+    ray_chunks = 4
+    """Training only: the rays are processed in this many chunks on two alternating side streams.  Autograd replays
+    each chunk's backward on its forward stream, so one chunk's table scatter (bound by L2 float reductions) overlaps
+    with the next chunk's tensor-core MLP backward (bound by its own latency chain, hardly touching L2)."""
+
+    def _field_chunk(self, rays: F.RayData, iv: F.SampleIntervals):
+        """hash encode + everything after it (ONE tcgen05 kernel forward, one backward) for a set of rays."""
+        features = self.hashgrid.encode_samples(rays, iv)
+        sh = self.direction_encoding(get_normalized_directions(rays.directions))
+        geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
+        return F.field_mlp(
+            features, sh, iv.num_samples,
+            [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight],
+            [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias],
+            self.sdf_to_density.beta, float(self.sdf_to_density.beta_min),
+        )
+
+    def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals):
+        N = rays.num_rays
+        k = self.ray_chunks if (torch.is_grad_enabled() and self.training and N >= 8192 * self.ray_chunks) else 1
+        if k <= 1:
+            return self._field_chunk(rays, iv)
+        dev = rays.origins.device
+        main = torch.cuda.current_stream(dev)
+        bounds = [(N * i) // k for i in range(k + 1)]
+        parts = []
+        for i in range(k):
+            lo, hi = bounds[i], bounds[i + 1]
+            sub = F.RayData(rays.origins[lo:hi], rays.directions[lo:hi], rays.pixel_area[lo:hi])
+            sub_iv = F.SampleIntervals(iv.starts[lo:hi], iv.ends[lo:hi])
+            side = F.side_stream(dev, i % 2)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                parts.append(self._field_chunk(sub, sub_iv))
+        outs = []
+        for s in (F.side_stream(dev, 0), F.side_stream(dev, 1)):
+            main.wait_stream(s)
+        for j in range(3):
+            for p in parts:
+                p[j].record_stream(main)
+            outs.append(torch.cat([p[j] for p in parts], dim=0))
+        return tuple(outs)
+
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
         if compute_normals:
             raise NotImplementedError("normals are not rendered on the NeuRadar path")
         rays, iv = per_ray_of(ray_samples)
         N, S = rays.num_rays, iv.num_samples
-        features = self.hashgrid.encode_samples(rays, iv)
         shape = tuple(ray_samples.shape) if len(ray_samples.shape) == 2 else (N, S)
         if self._tensor_core_path():
-            # everything after the hash grid in ONE tcgen05 kernel (and one for its backward)
-            sh = self.direction_encoding(get_normalized_directions(rays.directions))
-            geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
-            feature, sdf, alpha = F.field_mlp(
-                features, sh, S,
-                [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight],
-                [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias],
-                self.sdf_to_density.beta, float(self.sdf_to_density.beta_min),
-            )
+            feature, sdf, alpha = self._forward_tensor_core(rays, iv)
             return {
                 FieldHeadNames.FEATURE: feature.view(*shape, 32),
                 FieldHeadNames.SDF: sdf.view(*shape, 1),
                 FieldHeadNames.ALPHA: alpha.view(*shape, 1),
             }
+        features = self.hashgrid.encode_samples(rays, iv)
         geo = self.mlp_geo(features)
         geo_out, geo_embedding = torch.split(geo, [1, self.geo_feat_dim], dim=-1)
         # directions are per ray: evaluate the 16 SH values once per ray and broadcast over the samples

@@ -133,15 +133,32 @@ _WORKSPACES = {}
 
 
 def _workspace(nbytes: int, device):
-    """Scratch memory for kernels that want it (grown on demand, one buffer per device, reused across calls on the
-    same stream order)."""
+    """Scratch memory for kernels that want it: one buffer per (device, stream), grown on demand.  Calls on one stream
+    are ordered, so they can share a buffer; calls on different streams (the path overlaps its backward branches on
+    side streams) must not."""
     if nbytes <= 0:
         return None, 0
-    buf = _WORKSPACES.get(device)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _WORKSPACES.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty((nbytes,), device=device, dtype=torch.uint8)
-        _WORKSPACES[device] = buf
+        _WORKSPACES[key] = buf
     return buf.data_ptr(), nbytes
+
+
+_SIDE_STREAMS = {}
+
+
+def side_stream(device, index: int = 0) -> "torch.cuda.Stream":
+    """Per-device auxiliary streams.  Autograd replays every backward node on the stream its forward ran on, so
+    running independent branches of the forward on side streams is what lets their backward kernels overlap (the
+    latency-bound tensor-core MLP backward with the L2-reduction-bound table scatters)."""
+    key = (torch.device(device), index)
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = torch.cuda.Stream(device=device)
+        _SIDE_STREAMS[key] = s
+    return s
 
 
 # ------------------------------------------------------------------------------------------------

@@ -159,6 +159,24 @@ class ProposalNetworkSampler(Sampler):
         self._steps_since_update = 0
         self._step = 0
 
+    overlap_backward = True
+    """Run the proposal rounds on a side stream.  The forward is a dependent chain either way; the point is that
+    autograd replays each node on its forward stream, so the proposal backward (L2-reduction bound) then overlaps
+    with the main field's backward instead of queueing behind it."""
+
+    def _on_side_stream(self, fn, ray_samples):
+        dev = ray_samples.frustums.starts.device
+        if not (self.overlap_backward and torch.is_grad_enabled() and dev.type == "cuda"):
+            return fn()
+        main = torch.cuda.current_stream(dev)
+        side = F.side_stream(dev, 2)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            out = fn()
+        main.wait_stream(side)
+        out.record_stream(main)
+        return out
+
     def set_anneal(self, anneal: float) -> None:
         self._anneal = anneal
 
@@ -195,7 +213,7 @@ class ProposalNetworkSampler(Sampler):
                 fused = getattr(fn, "density_and_weights", None)
                 with torch.set_grad_enabled(updated and torch.is_grad_enabled()):
                     if fused is not None:  # proposal field of this package: density + weights in one kernel
-                        _, weights = fused(ray_samples)
+                        weights = self._on_side_stream(lambda: fused(ray_samples)[1], ray_samples)
                     else:
                         weights = ray_samples.get_weights(fn(ray_samples))
                 weights_list.append(weights)
