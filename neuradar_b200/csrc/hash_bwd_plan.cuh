@@ -49,9 +49,46 @@ __device__ __forceinline__ void scatter_row(float* __restrict__ base, uint32_t r
 struct BwdPlan {
   float* scratch;                   // replicated lattices, zeroed by the launcher
   int64_t offset[NRB_MAX_LEVELS];   // float offset of level l's first replica
+  int64_t stride[NRB_MAX_LEVELS];   // floats between replicas (multiple of 4: keeps vector reductions 16-byte aligned)
   int copies[NRB_MAX_LEVELS];       // 0/1: scatter straight into the table
   int r1[NRB_MAX_LEVELS];           // res + 1
 };
+
+// Two rows that differ only in the x corner (floor / ceil).  The x prime of the hash is 1, so whenever floor(x) is
+// even the two rows are r and r ^ 1: an aligned pair of adjacent table rows.  For F <= 2 the pair is then updated with
+// ONE reduction of twice the width (F32x2 for F = 1, F32x4 for F = 2) - the L2 reduction rate is per operation, not
+// per byte, so this removes a quarter of the operations on average.  The same holds for the dense lattice replicas
+// (x neighbours are adjacent, aligned when the lower index is even).
+template <int F>
+__device__ __forceinline__ void scatter_x_pair(float* __restrict__ base, uint32_t row_f, uint32_t row_c,
+                                               const float (&g)[F], float w_f, float w_c) {
+  if constexpr (F <= 2) {
+    if (row_c == (row_f ^ 1u)) {
+      const bool f_low = (row_f & 1u) == 0;
+      const float wl = f_low ? w_f : w_c, wh = f_low ? w_c : w_f;
+      float* p = base + static_cast<size_t>(row_f & ~1u) * F;
+      if constexpr (F == 1) {
+        atomicAdd(reinterpret_cast<float2*>(p), make_float2(g[0] * wl, g[0] * wh));
+      } else {
+        atomicAdd(reinterpret_cast<float4*>(p), make_float4(g[0] * wl, g[1] * wl, g[0] * wh, g[1] * wh));
+      }
+      return;
+    }
+  }
+  scatter_row<F>(base, row_f, g, w_f);
+  if (row_c != row_f || w_c != 0.0f) scatter_row<F>(base, row_c, g, w_c);
+}
+
+// corner order (common.cuh): 0:(c,c,c) 1:(c,f,c) 2:(f,f,c) 3:(f,c,c) 4:(c,c,f) 5:(c,f,f) 6:(f,f,f) 7:(f,c,f);
+// x pairs (floor, ceil): (3,0) (2,1) (7,4) (6,5)
+template <int F>
+__device__ __forceinline__ void scatter_rows8(float* __restrict__ base, const uint32_t (&row)[8], const float (&g)[F],
+                                              const float (&w)[8]) {
+  scatter_x_pair<F>(base, row[3], row[0], g, w[3], w[0]);
+  scatter_x_pair<F>(base, row[2], row[1], g, w[2], w[1]);
+  scatter_x_pair<F>(base, row[7], row[4], g, w[7], w[4]);
+  scatter_x_pair<F>(base, row[6], row[5], g, w[6], w[5]);
+}
 
 // Scatter the 8 corner contributions of one (point, level): into a replica when the level is replicated (and the
 // point lies inside the lattice), otherwise straight into the table.  `spread` picks the replica (warp index).
@@ -61,9 +98,8 @@ __device__ __forceinline__ void scatter_corners(const BwdPlan& plan, int l, int 
                                                 float* __restrict__ dtable, unsigned spread) {
   const int copies = plan.copies[l];
   if (copies > 1 && plan.r1[l] == 0) {  // replicas of the hashed level table
-    float* rep = plan.scratch + plan.offset[l] + (static_cast<size_t>(spread % static_cast<unsigned>(copies)) << log2_size) * F;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) scatter_row<F>(rep, c.row[k], gr, w[k]);
+    float* rep = plan.scratch + plan.offset[l] + static_cast<size_t>(spread % static_cast<unsigned>(copies)) * plan.stride[l];
+    scatter_rows8<F>(rep, c.row, gr, w);
     return;
   }
   if (copies > 1) {  // replicas of the dense vertex lattice
@@ -72,19 +108,18 @@ __device__ __forceinline__ void scatter_corners(const BwdPlan& plan, int l, int 
     const int xf = static_cast<int>(floorf(sx)), yf = static_cast<int>(floorf(sy)), zf = static_cast<int>(floorf(sz));
     const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
     if (xf >= 0 && yf >= 0 && zf >= 0 && xc < R1 && yc < R1 && zc < R1) {
-      float* rep = plan.scratch + plan.offset[l] +
-                   static_cast<size_t>(spread % static_cast<unsigned>(copies)) * (static_cast<size_t>(R1) * R1 * R1 * F);
+      float* rep = plan.scratch + plan.offset[l] + static_cast<size_t>(spread % static_cast<unsigned>(copies)) * plan.stride[l];
       const int cx[8] = {xc, xc, xf, xf, xc, xc, xf, xf};
       const int cy[8] = {yc, yf, yf, yc, yc, yf, yf, yc};
       const int cz[8] = {zc, zc, zc, zc, zf, zf, zf, zf};
+      uint32_t rows[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) scatter_row<F>(rep, static_cast<uint32_t>((cz[k] * R1 + cy[k]) * R1 + cx[k]), gr, w[k]);
+      for (int k = 0; k < 8; ++k) rows[k] = static_cast<uint32_t>((cz[k] * R1 + cy[k]) * R1 + cx[k]);
+      scatter_rows8<F>(rep, rows, gr, w);
       return;
     }
   }
-  float* base = dtable + (static_cast<size_t>(l) << log2_size) * F;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) scatter_row<F>(base, c.row[k], gr, w[k]);
+  scatter_rows8<F>(dtable + (static_cast<size_t>(l) << log2_size) * F, c.row, gr, w);
 }
 
 // Adds the replicas of every replicated level into the table: one thread per lattice vertex.
@@ -111,7 +146,7 @@ __global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constan
   for (int j = 0; j < F; ++j) sum[j] = 0.0f;
   for (int cpy = 0; cpy < plan.copies[l]; ++cpy) {
     float t[F];
-    load_row<F>(rep + static_cast<size_t>(cpy) * nv * F, 0, t);
+    load_row<F>(rep + static_cast<size_t>(cpy) * plan.stride[l], 0, t);
 #pragma unroll
     for (int j = 0; j < F; ++j) sum[j] += t[j];
   }
@@ -149,6 +184,7 @@ inline int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
   for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
     plan->copies[l] = 0;
     plan->offset[l] = 0;
+    plan->stride[l] = 0;
     plan->r1[l] = 0;
     if (l >= grid->num_levels || M < (int64_t{1} << 16)) continue;
     const int64_t r1 = static_cast<int64_t>(grid->scalings[l]) + 1;
@@ -164,7 +200,7 @@ inline int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
     } else {
       copies = static_cast<int>(scale * table_rows / verts + 0.5);
       copies = std::min(copies, 1024);
-      per_copy = r1 * r1 * r1 * F;
+      per_copy = (r1 * r1 * r1 * F + 3) & ~int64_t{3};
       plan->r1[l] = static_cast<int>(r1);
     }
     while (copies > 1 && static_cast<double>(copies) * per_copy * 4 > cap_mb * 1024 * 1024) --copies;
@@ -173,6 +209,7 @@ inline int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
       continue;
     }
     plan->copies[l] = copies;
+    plan->stride[l] = per_copy;
     plan->offset[l] = floats;
     floats += static_cast<int64_t>(copies) * per_copy;
     floats = (floats + 3) & ~int64_t{3};
