@@ -10,6 +10,7 @@
 // staged once per CTA.  Activations needed by the backward pass are written feature-major ([32][ld], coalesced
 // 128-byte warp stores) together with one bit mask per ReLU layer.
 #include <algorithm>
+#include <cstdlib>
 
 #include "tc_common.cuh"
 
@@ -302,7 +303,7 @@ __device__ __forceinline__ void commit_act_chunks(char* at_hi, char* at_lo, int 
 __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_constant__ FieldParams prm,
                                                                  const __grid_constant__ FieldBwdIn in,
                                                                  const __grid_constant__ FieldBwdOut out,
-                                                                 int samples_per_ray, int64_t M) {
+                                                                 int samples_per_ray, int64_t M, int dbg) {
   extern __shared__ __align__(128) char smem[];
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
   char* d_hi = smem + FieldBwdSmem::d_hi;
@@ -346,8 +347,9 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       issue_gemm(tmem_base, 128, acols, smem_u32(d_hi), smem_u32(d_lo), dcols, smem_u32(smem + field_w_hi(l)),
                  smem_u32(smem + field_w_lo(l)), kN[l], kred, false);
       mma_commit(mbar_data);
-      issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
-                 smem_u32(at_lo), kRows, kRows, !first);
+      if (!(dbg & 1))
+        issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
+                   smem_u32(at_lo), kRows, kRows, !first);
       mma_commit(mbar_dw);
     }
     dw_pending = true;
@@ -386,11 +388,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     for (int j = 0; j < 32; ++j) demb[j] = delta[j];  // residual branch
     wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
-    commit_act_chunks(at_hi, at_lo, t, pf);
+    if (!(dbg & 2)) store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    if (!(dbg & 8)) commit_act_chunks(at_hi, at_lo, t, pf);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
-    my_db[4 * 48 + lane] += warp_column_sums(tmp, lane);
+    if (!(dbg & 4)) my_db[4 * 48 + lane] += warp_column_sums(tmp, lane);
     issue_layer(4, 32, 32, 32);
     prefetch_act_chunks(in.g1, in.ld, row0, t, pf);
     wait_data();
@@ -400,11 +402,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     // ---- layer 3 (mlp_feature.layers.1): input g1
     wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
-    commit_act_chunks(at_hi, at_lo, t, pf);
+    if (!(dbg & 2)) store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    if (!(dbg & 8)) commit_act_chunks(at_hi, at_lo, t, pf);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
-    my_db[3 * 48 + lane] += warp_column_sums(tmp, lane);
+    if (!(dbg & 4)) my_db[3 * 48 + lane] += warp_column_sums(tmp, lane);
     issue_layer(3, 32, 32, 32);
     prefetch_act_chunks(in.emb, in.ld, row0, t, pf);
     wait_data();
@@ -414,9 +416,9 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     // ---- layer 2 (mlp_feature.layers.0): input [emb | sh]
     wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
-    commit_act_chunks(at_hi, at_lo, t, pf);
-    {  // rows 32..47 of the input^T tile: the ray's SH basis, 16 x 32 chunks, 4 per thread
+    if (!(dbg & 2)) store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    if (!(dbg & 8)) commit_act_chunks(at_hi, at_lo, t, pf);
+    if (!(dbg & 8)) {  // rows 32..47 of the input^T tile: the ray's SH basis, 16 x 32 chunks, 4 per thread
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int e = t + q * kRows;
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     }
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
-    my_db[2 * 48 + lane] += warp_column_sums(tmp, lane);
+    if (!(dbg & 4)) my_db[2 * 48 + lane] += warp_column_sums(tmp, lane);
     issue_layer(2, 32, 48, 32);
     prefetch_act_chunks(in.h1, in.ld, row0, t, pf);
     wait_data();
@@ -472,11 +474,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
       hi16[0] = demb[31];
 #pragma unroll
       for (int j = 1; j < 32; ++j) hi16[j] = 0.0f;
-      store_rows_transposed_split(dt_hi, dt_lo, warp, lane, lo32);
-      store_rows_transposed_split<4>(dt_hi, dt_lo, warp, lane, hi16, 32);  // rows 32..47 only
+      if (!(dbg & 2)) store_rows_transposed_split(dt_hi, dt_lo, warp, lane, lo32);
+      if (!(dbg & 2)) store_rows_transposed_split<4>(dt_hi, dt_lo, warp, lane, hi16, 32);  // rows 32..47 only
     }
-    commit_act_chunks(at_hi, at_lo, t, pf);
-    {
+    if (!(dbg & 8)) commit_act_chunks(at_hi, at_lo, t, pf);
+    if (!(dbg & 4)) {
       const float s0 = warp_sum(dsdf_v);
       if (lane == 0) my_db[1 * 48 + 0] += s0;
 #pragma unroll
@@ -493,11 +495,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     // ---- layer 0 (mlp_geo.layers.0): input x (row-major in memory: transposed through registers)
     wait_dw();
     store_row_split<32>(d_hi, d_lo, t, delta);
-    store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
-    store_rows_transposed_split(at_hi, at_lo, warp, lane, xrow);
+    if (!(dbg & 2)) store_rows_transposed_split(dt_hi, dt_lo, warp, lane, delta);
+    if (!(dbg & 2)) store_rows_transposed_split(at_hi, at_lo, warp, lane, xrow);
 #pragma unroll
     for (int j = 0; j < 32; ++j) tmp[j] = delta[j];
-    my_db[0 * 48 + lane] += warp_column_sums(tmp, lane);
+    if (!(dbg & 4)) my_db[0 * 48 + lane] += warp_column_sums(tmp, lane);
     issue_layer(0, 32, 32, 32);
     {
       const int64_t ntile = tile + gridDim.x;
@@ -750,7 +752,8 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
+  static const int dbg = std::getenv("NRB_FIELD_BWD_DEBUG") ? std::atoi(std::getenv("NRB_FIELD_BWD_DEBUG")) : 0;
   field_mlp_bwd_kernel<<<grid, tc::kRows, FieldBwdSmem::total, static_cast<cudaStream_t>(stream)>>>(
-      to_params(p), bi, bo, samples_per_ray, M);
+      to_params(p), bi, bo, samples_per_ray, M, dbg);
   return finish_launch("nrb_field_mlp_bwd");
 }
