@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(kRows) tc_probe_kernel(const float* __restrict
 // and layout conventions.  K in {32, 48}, N (padded) in {32, 48}.
 __global__ void __launch_bounds__(kRows) tc_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                           const float* __restrict__ b, int K, int n_out, int relu,
-                                                          int64_t M, float* __restrict__ y) {
+                                                          int64_t M, float* __restrict__ y, int dbg) {
   extern __shared__ __align__(128) char smem[];
   const int t = threadIdx.x, warp = t >> 5;
   const int N = (n_out + 15) & ~15;
@@ -622,27 +622,36 @@ __global__ void __launch_bounds__(kRows) tc_linear_kernel(const float* __restric
     float v[48];
 #pragma unroll
     for (int j = 0; j < 48; ++j) v[j] = (j < K) ? __ldg(x + rr * K + j) : 0.0f;
-    if (K == 32) {
-      float v32[32];
+    if (!(dbg & 2)) {
+      if (K == 32) {
+        float v32[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v32[j] = v[j];
-      store_row_split<32>(a_hi, a_lo, t, v32);
-    } else {
-      store_row_split<48>(a_hi, a_lo, t, v);
+        for (int j = 0; j < 32; ++j) v32[j] = v[j];
+        store_row_split<32>(a_hi, a_lo, t, v32);
+      } else {
+        store_row_split<48>(a_hi, a_lo, t, v);
+      }
     }
-    fence_async_smem();
+    if (!(dbg & 8)) fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (t == 0) {
-      fence_after_sync();
-      issue_gemm_kmajor(tmem_base, smem_u32(a_hi), smem_u32(a_lo), smem_u32(w_hi), smem_u32(w_lo), K, N, false);
-      mma_commit(mbar);
+    if (!(dbg & 1)) {
+      if (t == 0) {
+        fence_after_sync();
+        issue_gemm(tmem_base, 128, N, smem_u32(a_hi), smem_u32(a_lo), K, smem_u32(w_hi), smem_u32(w_lo), K, K, false);
+        mma_commit(mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1;
     }
-    mbar_wait(mbar, phase);
-    phase ^= 1;
     fence_after_sync();
     float acc[48];
-    tmem_load_row<48>(tmem_base, warp, 0, acc);
+    if (!(dbg & 4)) {
+      tmem_load_row<48>(tmem_base, warp, 0, acc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 48; ++j) acc[j] = v[j];
+    }
     if (ok) {
       for (int j = 0; j < n_out; ++j) {
         float r = acc[j] + (b != nullptr ? __ldg(b + j) : 0.0f);
@@ -670,7 +679,8 @@ extern "C" int nrb_tc_linear(const float* x, const float* w, const float* b, int
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
-  tc_linear_kernel<<<grid, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(x, w, b, K, n_out, relu, M, y);
+  static const int dbg = std::getenv("NRB_TC_LINEAR_DEBUG") ? std::atoi(std::getenv("NRB_TC_LINEAR_DEBUG")) : 0;
+  tc_linear_kernel<<<grid, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(x, w, b, K, n_out, relu, M, y, dbg);
   return finish_launch("nrb_tc_linear");
 }
 
