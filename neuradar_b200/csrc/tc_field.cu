@@ -140,17 +140,24 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   };
 
   const int64_t tiles = (M + kRows - 1) / kRows;
+  const int lane = t & 31;
+  // The operand tiles double as bounce buffers for the coalesced row I/O while no MMA is reading them: a warp's 32
+  // rows occupy exactly bytes [4096 w, 4096 (w+1)) of a 32-column tile, so warps never touch each other's part.
+  char* bounce_in = a_lo + warp * 4096;
+  char* bounce_out = a_hi + warp * 4096;
   float v[32];
-  if (static_cast<int64_t>(blockIdx.x) < tiles) load_row32(x + min(static_cast<int64_t>(blockIdx.x) * kRows + t, M - 1) * 32, v);
+  float4 xpf[8];  // this warp's 32 input rows, chunk-major, loaded one tile ahead
+  if (static_cast<int64_t>(blockIdx.x) < tiles)
+    warp_load_rows_coalesced(x, static_cast<int64_t>(blockIdx.x) * kRows + warp * 32, M, lane, xpf);
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row = tile * kRows + t;
     const bool ok = row < M;
     const int64_t rr = ok ? row : (M - 1);  // out-of-range rows compute on a valid row; only saved activations are stored
     // ---- mlp_geo layer 0: 32 -> 32, ReLU
+    warp_bounce_to_rows(bounce_in, lane, xpf, v);
     store_row_split<32>(a_hi, a_lo, t, v);
-    float xnext[32];  // prefetch the next tile's input row while this tile is in flight
     const int64_t ntile = tile + gridDim.x;
-    if (ntile < tiles) load_row32(x + min(ntile * kRows + t, M - 1) * 32, xnext);
+    if (ntile < tiles) warp_load_rows_coalesced(x, ntile * kRows + warp * 32, M, lane, xpf);
     run_layer(0);
     tmem_load_row<32>(tmem_base, warp, 0, v);
     const uint32_t m_h1 = relu_bias_mask(v, s_bias);
@@ -202,13 +209,11 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     tmem_load_row<32>(tmem_base, warp, 0, v);
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = emb[j] + (v[j] + s_bias[4 * 48 + j]);
+    warp_store_rows_coalesced(feature, tile * kRows + warp * 32, M, bounce_out, lane, v);  // last MMA is complete
     if (ok) {
-      store_row32(feature + row * 32, v);
       sdf[row] = sdf_v;
       alpha[row] = 1.0f / (1.0f + expf(sdf_v * beta));  // sigmoid(-sdf * beta)
     }
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = xnext[j];
   }
   fence_before_sync();
   __syncthreads();
@@ -261,7 +266,8 @@ struct FieldBwdSmem {
   static constexpr int at_hi = dt_lo + 48 * kRows * 4;  // input^T, [48 x 128]
   static constexpr int at_lo = at_hi + 48 * kRows * 4;
   static constexpr int dbacc = at_lo + 48 * kRows * 4;  // [4 warps][5 layers][48]
-  static constexpr int mbar = dbacc + 4 * 5 * 48 * 4;   // two mbarriers
+  static constexpr int bounce = dbacc + 4 * 5 * 48 * 4; // 4 warps x 4 KB for coalesced row I/O
+  static constexpr int mbar = bounce + 4 * 4096;        // two mbarriers
   static constexpr int tmem = mbar + 16;
   static constexpr int total = tmem + 8;
 };
@@ -335,6 +341,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   bool first = true, dw_pending = false;
   float dbeta_acc = 0.0f;
   float* my_db = dbacc + warp * 5 * 48;
+  char* bounce = smem + FieldBwdSmem::bounce + warp * 4096;
 
   // Tiles are staged (delta rows in d_*, delta^T in dt_*, input^T in at_*).  Issue both chains; the data chain is
   // committed first so that the next layer's delta does not wait for the (4x longer) weight-gradient chain.
@@ -378,7 +385,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     const uint32_t m_h1 = __ldg(in.masks + row), m_g1 = __ldg(in.masks + in.ld + row), m_g2 = __ldg(in.masks + 2 * in.ld + row);
     float delta[32], tmp[32];
     // ---- layer 4 (mlp_feature.layers.2): delta = d feature, input g2
-    load_row32(in.dfeature + rr * 32, delta);
+    {
+      float4 cpf[8];
+      warp_load_rows_coalesced(in.dfeature, row0 + warp * 32, M, lane, cpf);
+      warp_bounce_to_rows(bounce, lane, cpf, delta);
+    }
     if (!ok) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) delta[j] = 0.0f;
@@ -487,7 +498,11 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     }
     issue_layer(1, 48, 32, 40);
     float xrow[32];
-    load_row32(in.x + rr * 32, xrow);
+    {
+      float4 cpf[8];
+      warp_load_rows_coalesced(in.x, row0 + warp * 32, M, lane, cpf);
+      warp_bounce_to_rows(bounce, lane, cpf, xrow);
+    }
     wait_data();
     tmem_load_row<32>(tmem_base, warp, 0, delta);
 #pragma unroll
@@ -508,7 +523,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     wait_data();
     if (out.dx != nullptr) {
       tmem_load_row<32>(tmem_base, warp, 0, delta);
-      if (ok) store_row32(out.dx + row * 32, delta);
+      warp_store_rows_coalesced(out.dx, row0 + warp * 32, M, bounce, lane, delta);
     }
     first = false;
   }
