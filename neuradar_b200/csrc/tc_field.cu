@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
                                                                  int samples_per_ray, int64_t M,
                                                                  float* __restrict__ feature,  // [M,32]
                                                                  float* __restrict__ sdf,      // [M]
-                                                                 float* __restrict__ alpha) {  // [M]
+                                                                 float* __restrict__ alpha,    // [M]
+                                                                 int dbg) {
   extern __shared__ __align__(128) char smem[];
   const int t = threadIdx.x, warp = t >> 5;
   float* s_bias = reinterpret_cast<float*>(smem + FieldSmem::bias);
@@ -125,13 +126,15 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
 
   // one layer: operands are staged; fence, issue, wait for the accumulator
   auto run_layer = [&](int l) {
-    fence_async_smem();
+    if (!(dbg & 8)) fence_async_smem();
     fence_before_sync();
     __syncthreads();
+    if (dbg & 1) return;
     if (t == 0) {
       fence_after_sync();
-      issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
-                 smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
+      if (!(dbg & 2))
+        issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
+                   smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
       mma_commit(mbar);
     }
     mbar_wait(mbar, phase);
@@ -744,8 +747,9 @@ extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
+  static const int dbg = std::getenv("NRB_FIELD_FWD_DEBUG") ? std::atoi(std::getenv("NRB_FIELD_FWD_DEBUG")) : 0;
   field_mlp_fwd_kernel<<<grid, tc::kRows, FieldSmem::total, static_cast<cudaStream_t>(stream)>>>(
-      to_params(p), sv, x, sh, samples_per_ray, M, feature, sdf, alpha);
+      to_params(p), sv, x, sh, samples_per_ray, M, feature, sdf, alpha, dbg);
   return finish_launch("nrb_field_mlp_fwd");
 }
 
