@@ -56,6 +56,24 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       : "memory");
 }
 
+// One lane of a converged warp (CUTLASS's elect_one_sync): ptxas recognises the elected region as single-threaded and
+// emits straight-line UTCHMMA sequences; under a plain `threadIdx.x == 0` test it wraps every tcgen05.mma in an
+// ELECT / BRA.U.ANY loop (seen in SASS), which costs ~50 cycles per instruction.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// warp index that the compiler can prove warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(kFull, static_cast<int>(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ void mma_commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar))
                : "memory");

@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   const uint32_t a_hi_u = smem_u32(a_hi), a_lo_u = smem_u32(a_lo);
   const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
   const bool train = sv.h1 != nullptr;
+  const int uwarp = uniform_warp_idx();
   uint32_t phase = 0;
 
   // one layer: operands are staged; fence, issue, wait for the accumulator
@@ -130,12 +131,15 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     fence_before_sync();
     __syncthreads();
     if (dbg & 1) return;
-    if (t == 0) {
-      fence_after_sync();
-      if (!(dbg & 2))
-        issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
-                   smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
-      mma_commit(mbar);
+    if (uwarp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        if (!(dbg & 2))
+          issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
+                     smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase);
     phase ^= 1;
@@ -342,6 +346,7 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
   uint32_t phase_data = 0, phase_dw = 0;
   bool first = true, dw_pending = false;
+  const int uwarp = uniform_warp_idx();
   float dbeta_acc = 0.0f;
   float* my_db = dbacc + warp * 5 * 48;
   char* bounce = smem + FieldBwdSmem::bounce + warp * 4096;
@@ -352,15 +357,18 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (t == 0) {
-      fence_after_sync();
-      issue_gemm(tmem_base, 128, acols, smem_u32(d_hi), smem_u32(d_lo), dcols, smem_u32(smem + field_w_hi(l)),
-                 smem_u32(smem + field_w_lo(l)), kN[l], kred, false);
-      mma_commit(mbar_data);
-      if (!(dbg & 1))
-        issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
-                   smem_u32(at_lo), kRows, kRows, !first);
-      mma_commit(mbar_dw);
+    if (uwarp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        issue_gemm(tmem_base, 128, acols, smem_u32(d_hi), smem_u32(d_lo), dcols, smem_u32(smem + field_w_hi(l)),
+                   smem_u32(smem + field_w_lo(l)), kN[l], kred, false);
+        mma_commit(mbar_data);
+        if (!(dbg & 1))
+          issue_gemm(tmem_base + kDwCol[l], 64, acols, smem_u32(dt_hi), smem_u32(dt_lo), kRows, smem_u32(at_hi),
+                     smem_u32(at_lo), kRows, kRows, !first);
+        mma_commit(mbar_dw);
+      }
+      __syncwarp();
     }
     dw_pending = true;
   };
