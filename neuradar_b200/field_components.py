@@ -236,10 +236,27 @@ class NoActors:
     n_actors = 0
 
 
+def _pose_inverse(pose: Tensor) -> Tensor:
+    """[..., 3|4, 4] -> [..., 3, 4] (utils/poses.py:42-55)."""
+    Ri = pose[..., :3, :3].transpose(-2, -1)
+    return torch.cat([Ri, -Ri.matmul(pose[..., :3, 3:])], dim=-1)
+
+
+def _transform(points: Tensor, transforms: Tensor, with_translation: bool = True) -> Tensor:
+    """cameras/lidars.py:507-519"""
+    out = (points.unsqueeze(-2) @ transforms[..., :3, :3].swapaxes(-2, -1)).squeeze(-2)
+    return out + transforms[..., :3, 3] if with_translation else out
+
+
 class NeuRADHashEncoding(nn.Module):
-    """Static-world hash grid with contraction and per-level anti-alias weights
-    (neurad_encoding.py:87-189,277-280,309-316).  Dynamic actors are row "next-3" of SURVEY.md 8f and are not
-    part of this round: constructing with n_actors > 0 raises."""
+    """Static-world hash grid plus per-actor grids with contraction and per-level anti-alias weights
+    (neurad_encoding.py:87-316, the torch path: one 3-D grid per actor).
+
+    `dynamic_actors` is the reference's `DynamicActors` (or anything with `n_actors`, `get_boxes2world(times,
+    flatten=False) -> (boxes2world [N,A,4,4], valid [N,A])`, `actor_bounds() -> [A,3]` and `actor_to_id [A]`); its
+    trajectory interpolation is outside the hot path and is used as is.  The static grid runs through the
+    gaussian+contraction and hash kernels; the actor branch keeps the reference's bookkeeping (which samples fall
+    into which box) in PyTorch index ops and evaluates the per-actor grids with the same hash kernels."""
 
     def __init__(self, config: NeuRADHashEncodingConfig, dynamic_actors=None, static_scale: float = 1.0,
                  implementation: str = "b200") -> None:
@@ -248,9 +265,8 @@ class NeuRADHashEncoding(nn.Module):
         self.config = config
         self.implementation = implementation
         self.actors = dynamic_actors if dynamic_actors is not None else NoActors()
-        if getattr(self.actors, "n_actors", 0) > 0 and not config.disable_actors:
-            raise NotImplementedError("dynamic-actor grids are not implemented yet (SURVEY.md 8f, next-3)")
         self.static_scale = float(static_scale)
+        self.actor_scale = float(config.actor.actor_scale)
         self.static_grid = HashEncoding(
             features_per_level=config.static.hashgrid_dim,
             num_levels=config.static.num_levels,
@@ -258,7 +274,19 @@ class NeuRADHashEncoding(nn.Module):
             max_res=config.static.max_res,
             log2_hashmap_size=config.static.log2_hashmap_size,
         )
-        self.actor_grids = nn.ModuleList([])
+        n_grids = int(getattr(self.actors, "n_actors", 0))
+        self.actor_grids = nn.ModuleList(
+            [
+                HashEncoding(
+                    features_per_level=config.actor.hashgrid_dim,
+                    num_levels=config.actor.num_levels,
+                    min_res=config.actor.base_res,
+                    max_res=config.actor.max_res,
+                    log2_hashmap_size=config.actor.log2_hashmap_size,
+                )
+                for _ in range(n_grids)
+            ]
+        )
         self.scene_repr_dim = self.static_grid.get_out_dim()
 
     def get_out_dim(self) -> int:
@@ -267,24 +295,108 @@ class NeuRADHashEncoding(nn.Module):
     def get_param_groups(self, param_groups: Dict):
         param_groups["hashgrids"] += list(self.static_grid.parameters()) + list(self.actor_grids.parameters())
 
+    @property
+    def has_actors(self) -> bool:
+        return int(getattr(self.actors, "n_actors", 0)) > 0 and not self.config.disable_actors
+
     def forward(self, positions: GaussiansStd, times: Optional[Tensor] = None, directions: Optional[Tensor] = None):
         """World-space gaussians (mean [N,S,1,3], std [N,S,1,1]) -> (features [N*S, L*F], directions)."""
         mean = positions.mean.reshape(-1, 3)
         std = positions.std.reshape(-1, 1)
-        # ScaledSceneContraction(order=inf, scale=static_scale), spatial_distortions.py:103-113,132-136
-        mean = mean / self.static_scale
-        std = std / self.static_scale
+        feats = self.static_grid(*self._contract(mean, std, self.static_scale))
+        if not self.has_actors or times is None:
+            return feats, directions
+        n, s = positions.mean.shape[0], positions.mean.shape[1]
+        dirs = None if directions is None else directions.reshape(n, s, 3)
+        feats, dirs = self._apply_actors(feats, positions.mean.reshape(n, s, 3), positions.std.reshape(n, s, 1), dirs,
+                                         times.reshape(n, -1)[:, 0])
+        return feats, (None if dirs is None else dirs.reshape(directions.shape))
+
+    @staticmethod
+    def _contract(mean: Tensor, std: Tensor, scale: float) -> Tuple[Tensor, Tensor]:
+        """ScaledSceneContraction(order=inf, scale) on GaussiansStd, spatial_distortions.py:103-113,132-136."""
+        mean = mean / scale
+        std = std / scale
         mag = mean.abs().amax(dim=-1, keepdim=True)
         cm = mag.clamp_min(1.0)
         inside = mag < 1
         mean = torch.where(inside, mean, (2 - (1 / cm)) * (mean / cm))
         std = torch.where(inside, std, std * ((2 * cm - 1).pow(1 / 3) / cm) ** 2)
-        mean = (mean + 2.0) / 4.0
-        std = std / 4.0
-        feats = self.static_grid(mean, std=std)
-        return feats, directions
+        return (mean + 2.0) / 4.0, std / 4.0
 
-    def encode_samples(self, rays: F.RayData, iv: F.SampleIntervals) -> Tensor:
-        """Fast path from per-ray data: gaussians + contraction in one kernel, then the weighted hash encode."""
+    def encode_samples(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
+        """Fast path from per-ray data.  Returns (features [N*S, L*F], per-sample directions [N,S,3] or None when no
+        sample was claimed by an actor and the per-ray directions still apply)."""
         x, std = F.frustum_gaussians(rays, iv, self.static_scale)
-        return F.hash_encode(x, self.static_grid.hash_table, self.static_grid.spec, std, samples_per_ray=iv.num_samples)
+        feats = F.hash_encode(x, self.static_grid.hash_table, self.static_grid.spec, std, samples_per_ray=iv.num_samples)
+        if not self.has_actors or times is None:
+            return feats, None
+        # world-space gaussians of cameras/rays.py:109-124 for the actor bookkeeping
+        starts, ends = iv.starts, iv.ends
+        dist = (ends - starts) / 2
+        t = starts + dist
+        mean = rays.origins[:, None, :] + rays.directions[:, None, :] * t[..., None]
+        wstd = (rays.pixel_area[:, None, None] * t[..., None].pow(2) * dist[..., None]).pow(1 / 3)
+        dirs = rays.directions[:, None, :].expand(-1, iv.num_samples, -1)
+        return self._apply_actors(feats, mean, wstd, dirs, times.reshape(-1))
+
+    @torch.no_grad()
+    def _actor_indices(self, mean: Tensor, boxes2world: Tensor, valid: Tensor, world2boxes: Tensor, bounds: Tensor):
+        """(ray, sample, actor) of the samples inside actor boxes: ray line vs bounding sphere, sample vs sphere, then
+        the exact box test (neurad_encoding.py:231-275)."""
+        eps = 1.0e-7
+        radii = bounds.norm(dim=-1)
+        p0 = mean[:, 0, :]
+        line = mean[:, -1, :] - p0
+        line = (line / (torch.linalg.norm(line, dim=-1, keepdim=True) + eps)).unsqueeze(-2)
+        centers = boxes2world[..., :3, 3]
+        dist = torch.linalg.norm(torch.cross(centers - p0.unsqueeze(-2), line.expand_as(centers), dim=-1), dim=-1)
+        r, a = ((dist < radii) & valid).nonzero(as_tuple=False).T
+        if r.shape[0] == 0:
+            return r, r, r
+        within = torch.linalg.norm(mean[r] - centers[r, a].unsqueeze(-2), dim=-1) < radii[a].unsqueeze(-1)
+        k, s = within.nonzero(as_tuple=False).T
+        ri, ai = r[k], a[k]
+        inside = (_transform(mean[ri, s], world2boxes[ri, ai]).abs() < bounds[ai]).all(dim=-1)
+        return ri[inside], s[inside], ai[inside]
+
+    def _apply_actors(self, feats: Tensor, mean: Tensor, std: Tensor, dirs: Optional[Tensor], times: Tensor,
+                      ray_flip: Optional[Tensor] = None):
+        """Overwrite the features (and directions) of the samples that fall into an actor box
+        (neurad_encoding.py:176-229,295-316).  mean [N,S,3], std [N,S,1] in world units."""
+        n, s, _ = mean.shape
+        grad_ctx = torch.enable_grad() if self.config.require_actor_grad else torch.no_grad()
+        with grad_ctx:
+            boxes2world, valid = self.actors.get_boxes2world(times, flatten=False)
+            world2boxes = _pose_inverse(boxes2world)
+            ri, si, ai = self._actor_indices(mean.detach(), boxes2world.detach(), valid, world2boxes.detach(),
+                                             self.actors.actor_bounds())
+            if ri.shape[0] == 0:
+                return feats, None
+            w2b = world2boxes[ri, ai]
+            pos = _transform(mean[ri, si], w2b)
+            new_dirs = None
+            if dirs is not None:
+                d = _transform(dirs[ri, si], w2b, with_translation=False)
+                d = d / (torch.linalg.norm(d, dim=-1, keepdim=True) + 1.0e-7)
+            if self.training and self.config.actor.flip_prob > 1.0e-7:
+                if ray_flip is None:  # -1 with probability flip_prob, per ray (neurad_encoding.py:218-225)
+                    ray_flip = torch.bernoulli(torch.full((n,), self.config.actor.flip_prob, device=mean.device)) * -2 + 1
+                f = ray_flip.to(pos.dtype)[ri][:, None]
+                pos = torch.cat([pos[:, :1] * f, pos[:, 1:]], dim=-1)
+                if dirs is not None:
+                    d = torch.cat([d[:, :1] * f, d[:, 1:]], dim=-1)
+            if dirs is not None:
+                new_dirs = dirs.clone()
+                new_dirs[ri, si] = d
+        cpos, cstd = self._contract(pos, std[ri, si], self.actor_scale)
+        grid_id = self.actors.actor_to_id[ai]
+        out_dim = self.scene_repr_dim
+        actor_feats = torch.zeros((ri.shape[0], out_dim), device=feats.device, dtype=feats.dtype)
+        for gid in grid_id.unique().tolist():  # per-actor grids, as the reference's torch path (neurad_encoding.py:295-307)
+            grid = self.actor_grids[gid]
+            sel = (grid_id == gid).nonzero(as_tuple=True)[0]
+            f = grid(cpos[sel], std=cstd[sel])
+            actor_feats = actor_feats.index_put((sel,), torch.nn.functional.pad(f, (0, out_dim - f.shape[-1])))
+        feats = feats.view(n, s, out_dim).index_put((ri, si), actor_feats).view(n * s, out_dim)
+        return feats, new_dirs

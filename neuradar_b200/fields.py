@@ -113,23 +113,28 @@ class NeuRADField(nn.Module):
     with the next chunk's tensor-core MLP backward.  Measured on B200 (config 2): 11.97 ms/step unchunked, 11.71 ms
     with 2 chunks, 12.9 ms with 4 (per-chunk workspace clears and folds eat the overlap) - left off."""
 
-    def _field_chunk(self, rays: F.RayData, iv: F.SampleIntervals):
+    def _field_chunk(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         """hash encode + everything after it (ONE tcgen05 kernel forward, one backward) for a set of rays."""
-        features = self.hashgrid.encode_samples(rays, iv)
-        sh = self.direction_encoding(get_normalized_directions(rays.directions))
+        features, sample_dirs = self.hashgrid.encode_samples(rays, iv, times)
+        if sample_dirs is None:  # directions are per ray: 16 SH values per ray, indexed by row / S in the kernel
+            sh = self.direction_encoding(get_normalized_directions(rays.directions))
+            sh_group = iv.num_samples
+        else:  # some samples were rotated into an actor frame: one SH row per sample
+            sh = self.direction_encoding(get_normalized_directions(sample_dirs.reshape(-1, 3)))
+            sh_group = 1
         geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
         return F.field_mlp(
-            features, sh, iv.num_samples,
+            features, sh, sh_group,
             [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight],
             [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias],
             self.sdf_to_density.beta, float(self.sdf_to_density.beta_min),
         )
 
-    def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals):
+    def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         N = rays.num_rays
         k = self.ray_chunks if (torch.is_grad_enabled() and self.training and N >= 8192 * self.ray_chunks) else 1
-        if k <= 1:
-            return self._field_chunk(rays, iv)
+        if k <= 1 or self.hashgrid.has_actors:
+            return self._field_chunk(rays, iv, times)
         dev = rays.origins.device
         main = torch.cuda.current_stream(dev)
         bounds = [(N * i) // k for i in range(k + 1)]
@@ -157,19 +162,26 @@ class NeuRADField(nn.Module):
         rays, iv = per_ray_of(ray_samples)
         N, S = rays.num_rays, iv.num_samples
         shape = tuple(ray_samples.shape) if len(ray_samples.shape) == 2 else (N, S)
+        times = None
+        if self.hashgrid.has_actors:
+            if ray_samples.times is None:
+                raise ValueError("ray_samples.times is required in a scene with dynamic actors")
+            times = ray_samples.times.reshape(N, -1)[:, 0]
         if self._tensor_core_path():
-            feature, sdf, alpha = self._forward_tensor_core(rays, iv)
+            feature, sdf, alpha = self._forward_tensor_core(rays, iv, times)
             return {
                 FieldHeadNames.FEATURE: feature.view(*shape, 32),
                 FieldHeadNames.SDF: sdf.view(*shape, 1),
                 FieldHeadNames.ALPHA: alpha.view(*shape, 1),
             }
-        features = self.hashgrid.encode_samples(rays, iv)
+        features, sample_dirs = self.hashgrid.encode_samples(rays, iv, times)
         geo = self.mlp_geo(features)
         geo_out, geo_embedding = torch.split(geo, [1, self.geo_feat_dim], dim=-1)
-        # directions are per ray: evaluate the 16 SH values once per ray and broadcast over the samples
-        sh = self.direction_encoding(get_normalized_directions(rays.directions))
-        sh = sh[:, None, :].expand(N, S, 16).reshape(N * S, 16)
+        if sample_dirs is None:  # per-ray directions: 16 SH values per ray, broadcast over the samples
+            sh = self.direction_encoding(get_normalized_directions(rays.directions))
+            sh = sh[:, None, :].expand(N, S, 16).reshape(N * S, 16)
+        else:
+            sh = self.direction_encoding(get_normalized_directions(sample_dirs.reshape(-1, 3)))
         feature = geo_embedding + self.mlp_feature(torch.cat([geo_embedding, sh], dim=-1))
         outputs = {FieldHeadNames.FEATURE: feature.view(*shape, self.config.nff_out_dim)}
         geo_out = geo_out.reshape(*shape, 1)
@@ -215,6 +227,12 @@ class NeuRADProposalField(nn.Module):
     def density_and_weights(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
         """One kernel for get_density + RaySamples.get_weights: ([N,S,1], [N,S,1])."""
         rays, iv = per_ray_of(ray_samples)
+        if self.hashgrid.has_actors:  # unfused: the actor branch rewrites features between the grid and the decoder
+            if ray_samples.times is None:
+                raise ValueError("ray_samples.times is required in a scene with dynamic actors")
+            feats, _ = self.hashgrid.encode_samples(rays, iv, ray_samples.times.reshape(rays.num_rays, -1)[:, 0])
+            dens = trunc_exp(self.density_decoder(feats)).view(rays.num_rays, iv.num_samples)
+            return dens.unsqueeze(-1), F.density_weights(dens, iv).unsqueeze(-1)
         grid = self.hashgrid.static_grid
         dens, w = F.proposal_round(grid.hash_table, self.density_decoder.weight, rays, iv, grid.spec,
                                    self.hashgrid.static_scale)

@@ -526,3 +526,100 @@ def bench_loss(out: PathOutputs) -> Tensor:
     for w in out.weights_list[:-1]:
         loss = loss + w.pow(2).mean()
     return loss
+
+
+# --------------------------------------------------------------------------------------------
+# H8: dynamic actors (field_components/neurad_encoding.py:152-307)
+# --------------------------------------------------------------------------------------------
+def pose_inverse(pose: Tensor) -> Tensor:
+    """[..., 3|4, 4] -> [..., 3, 4] inverse of a rigid transform (utils/poses.py:42-55)."""
+    R = pose[..., :3, :3]
+    t = pose[..., :3, 3:]
+    Ri = R.transpose(-2, -1)
+    return torch.cat([Ri, -Ri.matmul(t)], dim=-1)
+
+
+def transform_points(points: Tensor, transforms: Tensor, with_translation: bool = True) -> Tensor:
+    """cameras/lidars.py:507-519."""
+    out = (points.unsqueeze(-2) @ transforms[..., :3, :3].swapaxes(-2, -1)).squeeze(-2)
+    return out + transforms[..., :3, 3] if with_translation else out
+
+
+def actor_sample_indices(mean: Tensor, boxes2world: Tensor, valid: Tensor, bounds: Tensor) -> Tuple[Tensor, Tensor, Tensor]:
+    """(ray, sample, actor) triples of the samples inside actor boxes (neurad_encoding.py:231-275).
+
+    mean [N,S,3] world-space sample centres, boxes2world [N,A,4,4] at each ray's time, valid [N,A], bounds [A,3]."""
+    eps = 1.0e-7
+    radii = bounds.norm(dim=-1)
+    p0 = mean[:, 0, :]
+    line = mean[:, -1, :] - p0
+    line = (line / (torch.linalg.norm(line, dim=-1, keepdim=True) + eps)).unsqueeze(-2)
+    centers = boxes2world[..., :3, 3]
+    dist = torch.linalg.norm(torch.cross(centers - p0.unsqueeze(-2), line.expand_as(centers), dim=-1), dim=-1)
+    r, a = ((dist < radii) & valid).nonzero(as_tuple=False).T
+    empty = torch.empty(0, dtype=torch.int64)
+    if r.shape[0] == 0:
+        return empty, empty, empty
+    within = torch.linalg.norm(mean[r] - centers[r, a].unsqueeze(-2), dim=-1) < radii[a].unsqueeze(-1)
+    k, s = within.nonzero(as_tuple=False).T
+    ri, ai = r[k], a[k]
+    w2b = pose_inverse(boxes2world)
+    inside = (transform_points(mean[ri, s], w2b[ri, ai]).abs() < bounds[ai]).all(dim=-1)
+    return ri[inside], s[inside], ai[inside]
+
+
+def neurad_hash_encode_with_actors(
+    mean: Tensor, std: Tensor, directions: Tensor, static: GridParams, actor_grids: Sequence[GridParams],
+    static_scale: float, actor_scale: float, boxes2world: Tensor, valid: Tensor, bounds: Tensor, actor_to_id: Tensor,
+    ray_flip: Optional[Tensor] = None,
+) -> Tuple[Tensor, Tensor]:
+    """NeuRADHashEncoding.forward with per-actor 3-D grids (the torch path, neurad_encoding.py:152-229,295-316).
+
+    mean [N,S,3], std [N,S,1] world-space gaussians, directions [N,S,3]; ray_flip [N] of +-1 (training) or None.
+    Returns features [N*S, L*F] and the per-sample directions (actor samples rotated into the box frame)."""
+    n, s, _ = mean.shape
+    feats = neurad_hash_encode(mean, std, static.table, static.scalings, static.log2_hashmap_size, static_scale)
+    ri, si, ai = actor_sample_indices(mean, boxes2world, valid, bounds)
+    directions = directions.clone()
+    if ri.shape[0] == 0:
+        return feats, directions
+    w2b = pose_inverse(boxes2world)[ri, ai]
+    pos = transform_points(mean[ri, si], w2b)
+    d = transform_points(directions[ri, si], w2b, with_translation=False)
+    d = d / (torch.linalg.norm(d, dim=-1, keepdim=True) + 1.0e-7)
+    if ray_flip is not None:
+        f = ray_flip[ri]
+        pos = torch.cat([pos[:, :1] * f[:, None], pos[:, 1:]], dim=-1)
+        d = torch.cat([d[:, :1] * f[:, None], d[:, 1:]], dim=-1)
+    directions[ri, si] = d
+    cpos, cstd = contract(pos, std[ri, si], actor_scale)
+    out_dim = feats.shape[-1]
+    grid_id = actor_to_id[ai]
+    actor_feats = torch.zeros((ri.shape[0], out_dim))
+    for gid in grid_id.unique():
+        g = actor_grids[int(gid)]
+        m = grid_id == gid
+        f = hash_encode(cpos[m], g.table, g.scalings, g.log2_hashmap_size)
+        w = level_weights(g.scalings, cstd[m])
+        f = (f.view(f.shape[0], g.scalings.numel(), -1) * w[..., None]).flatten(-2, -1)
+        actor_feats = actor_feats.index_put((m.nonzero(as_tuple=True)[0],), torch.nn.functional.pad(f, (0, out_dim - f.shape[-1])))
+    feats = feats.view(n, s, out_dim).index_put((ri, si), actor_feats)
+    return feats.view(n * s, out_dim), directions
+
+
+def field_forward_with_actors(p: FieldParams, actor_grids: Sequence[GridParams], actor_scale: float, origins: Tensor,
+                              directions: Tensor, pixel_area: Tensor, starts: Tensor, ends: Tensor, boxes2world: Tensor,
+                              valid: Tensor, bounds: Tensor, actor_to_id: Tensor, ray_flip: Optional[Tensor] = None):
+    """NeuRADField.forward (fields/neurad_field.py:128-152) in a scene with dynamic actors."""
+    n, s = starts.shape
+    mean, std = fast_isotropic_gaussian(origins, directions, starts, ends, pixel_area)
+    dirs = directions[:, None, :].expand(n, s, 3)
+    feats, dirs = neurad_hash_encode_with_actors(mean, std, dirs, p.grid, actor_grids, p.static_scale, actor_scale,
+                                                 boxes2world, valid, bounds, actor_to_id, ray_flip)
+    geo = mlp(feats, p.geo_w, p.geo_b)
+    sdf, emb = torch.split(geo, [1, geo.shape[-1] - 1], dim=-1)
+    dir_emb = sh16((dirs.reshape(-1, 3) + 1.0) / 2.0)
+    feature = emb + mlp(torch.cat([emb, dir_emb], dim=-1), p.feat_w, p.feat_b)
+    sdf = sdf.view(n, s, 1)
+    alpha = torch.sigmoid(-sdf * (p.beta.abs() + p.beta_min))
+    return {"feature": feature.view(n, s, -1), "sdf": sdf, "alpha": alpha, "grid_features": feats, "directions": dirs}

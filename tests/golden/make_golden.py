@@ -348,8 +348,97 @@ def gen_path():
     save("path", **out)
 
 
-if __name__ == "__main__":
+def _main_all():
     gen_hash()
     gen_small_kats()
     gen_samplers()
     gen_path()
+
+
+def synth_trajectories(n_actors=3, n_times=6):
+    """Non-overlapping boxes moving on straight lines with a slow yaw."""
+    import math
+
+    trajs = []
+    ts = torch.linspace(0.0, 2.0, n_times)
+    for a in range(n_actors):
+        poses = torch.eye(4).repeat(n_times, 1, 1)
+        for i, t in enumerate(ts):
+            yaw = 0.3 * a + 0.1 * float(t)
+            c, s = math.cos(yaw), math.sin(yaw)
+            poses[i, :3, :3] = torch.tensor([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+            poses[i, :3, 3] = torch.tensor([8.0 + 9.0 * a + 1.5 * float(t), -6.0 + 6.0 * a, 0.9])
+        trajs.append({"poses": poses, "timestamps": ts.clone(), "dims": torch.tensor([2.0, 4.6, 1.7]),
+                      "symmetric": True, "deformable": False})
+    return trajs
+
+
+def gen_actors():
+    """NeuRADHashEncoding / NeuRADField with dynamic actors (neurad_encoding.py:152-307), eval and training mode."""
+    torch.manual_seed(31)
+    trajs = synth_trajectories()
+    actors = DynamicActors(DynamicActorsConfig(), trajectories=trajs)
+    fcfg = NeuRADFieldConfig(
+        grid=NeuRADHashEncodingConfig(
+            static=StaticSettings(hashgrid_dim=2, num_levels=16, base_res=16, max_res=1024, log2_hashmap_size=10),
+            actor=ActorSettings(flip_prob=0.25, log2_hashmap_size=9),
+        )
+    )
+    fld = NeuRADField(fcfg, actors, static_scale=100.0, implementation="torch")
+    with torch.no_grad():
+        fld.hashgrid.static_grid.hash_table.mul_(300.0)
+        for g_ in fld.hashgrid.actor_grids:
+            g_.hash_table.mul_(300.0)
+    N, S = 96, 32
+    g = torch.Generator().manual_seed(32)
+    origins = torch.tensor([0.0, 0.0, 1.5]) + torch.randn((N, 3), generator=g) * torch.tensor([1.0, 1.0, 0.2])
+    times = torch.rand((N, 1), generator=g) * 2.0
+    # aim most rays at an actor (position at the ray's time, roughly), the rest anywhere
+    target = torch.stack([torch.tensor([8.0 + 9.0 * (i % 3) + 1.5, -6.0 + 6.0 * (i % 3), 0.9]) for i in range(N)])
+    target = target + torch.randn((N, 3), generator=g) * torch.tensor([1.5, 0.8, 0.5])
+    d = target - origins
+    d[::5] = torch.randn((len(d[::5]), 3), generator=g)
+    directions = d / d.norm(dim=-1, keepdim=True)
+    pixel_area = torch.full((N, 1), 4.5e-6)
+    bins = torch.linspace(0.0, 40.0, S + 1).expand(N, S + 1).contiguous() + torch.rand((N, 1), generator=g) * 0.3
+    rb = RayBundle(origins=origins, directions=directions, pixel_area=pixel_area, times=times, metadata={})
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    out = dict(origins=origins, directions=directions, pixel_area=pixel_area, times=times, bins=bins,
+               actor_bounds=actors.actor_bounds(), actor_to_id=actors.actor_to_id)
+    out.update({f"p_{k.replace('.', '__')}": v for k, v in fld.state_dict().items() if "actors" not in k})
+    for mode in ("eval", "train"):
+        fld.train(mode == "train")
+        actors.train(mode == "train")
+        fld.zero_grad()
+        boxes2world, valid = actors.get_boxes2world(times[:, 0], flatten=False)
+        out[f"{mode}_boxes2world"], out[f"{mode}_valid"] = boxes2world, valid
+        torch.manual_seed(5)
+        flips = torch.bernoulli(torch.full((N,), 0.25)) * -2 + 1
+        torch.manual_seed(5)
+        gaussians = rs.frustums.get_fast_isotropic_gaussian(1)
+        feats, dirs = fld.hashgrid(gaussians, rs.times, rs.frustums.directions)
+        out[f"{mode}_grid_features"], out[f"{mode}_grid_directions"] = feats, dirs
+        if mode == "train":
+            out["train_ray_flip"] = flips
+        torch.manual_seed(5)
+        fo = fld(rs)
+        out[f"{mode}_feature"], out[f"{mode}_sdf"], out[f"{mode}_alpha"] = (
+            fo[FieldHeadNames.FEATURE], fo[FieldHeadNames.SDF], fo[FieldHeadNames.ALPHA])
+        if mode == "train":
+            gf = torch.randn(fo[FieldHeadNames.FEATURE].shape, generator=g)
+            ga = torch.randn(fo[FieldHeadNames.ALPHA].shape, generator=g)
+            out["train_gf"], out["train_ga"] = gf, ga
+            ((fo[FieldHeadNames.FEATURE] * gf).sum() + (fo[FieldHeadNames.ALPHA] * ga).sum()).backward()
+            out["train_d_static_table"] = fld.hashgrid.static_grid.hash_table.grad
+            for i, g_ in enumerate(fld.hashgrid.actor_grids):
+                out[f"train_d_actor_table{i}"] = g_.hash_table.grad if g_.hash_table.grad is not None else torch.zeros_like(g_.hash_table)
+            out["train_d_geo_w0"] = fld.mlp_geo.layers[0].weight.grad
+    n_inside = int((out["eval_grid_features"][:, 16:] == 0).all(dim=-1).sum())
+    print("samples inside actor boxes:", n_inside, "of", N * S)
+    save("actors", **out)
+
+
+if __name__ == "__main__":
+    if "--actors-only" not in sys.argv:
+        _main_all()
+    gen_actors()

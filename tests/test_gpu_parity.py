@@ -535,3 +535,72 @@ def test_config5_inference_sweep(nb):
     pts = O.radar_points(depth[:512].cpu(), theta, phi)
     assert rel_err(pts, O.radar_points(ref.depth, theta, phi)) <= 1e-3
     assert rel_err(pts, d * depth[:512].cpu()) <= 1e-5  # unit directions: the point head is direction * depth
+
+
+# ------------------------------------------------------------------------------------------------ dynamic actors (H8)
+class GoldenActors(torch.nn.Module):
+    """Stand-in for the reference's DynamicActors (trajectory interpolation is outside the path): replays the
+    boxes2world / valid tensors the reference produced for the golden rays."""
+
+    def __init__(self, g, mode, device):
+        super().__init__()
+        self.n_actors = 3
+        self.b2w = g[f"{mode}_boxes2world"].to(device)
+        self.valid = g[f"{mode}_valid"].to(device)
+        self.bounds = g["actor_bounds"].to(device)
+        self.actor_to_id = g["actor_to_id"].to(device)
+
+    def get_boxes2world(self, query_times, flatten=True):
+        assert not flatten and query_times.shape[0] == self.b2w.shape[0]
+        return self.b2w, self.valid
+
+    def actor_bounds(self):
+        return self.bounds
+
+
+@pytest.mark.parametrize("mode", ["eval", "train"])
+def test_dynamic_actor_branch_golden(nb, golden, mode):
+    """NeuRADField in a scene with dynamic actors against the reference's own outputs (tests/golden/actors.npz)."""
+    import neuradar_b200 as pkg
+
+    g = golden("actors")
+    actors = GoldenActors(g, mode, DEV)
+    cfg = pkg.NeuRADFieldConfig(grid=pkg.NeuRADHashEncodingConfig(
+        static=pkg.StaticSettings(hashgrid_dim=2, num_levels=16, base_res=16, max_res=1024, log2_hashmap_size=10),
+        actor=pkg.ActorSettings(flip_prob=0.25, log2_hashmap_size=9)))
+    fld = pkg.NeuRADField(cfg, actors=actors, static_scale=100.0).to(DEV)
+    sd = {k[2:].replace("__", "."): v for k, v in g.items() if k.startswith("p_")}
+    res = fld.load_state_dict(sd, strict=False)
+    assert not res.unexpected_keys and not res.missing_keys
+    fld.train(mode == "train")
+    bins = g["bins"].to(DEV)
+    rb = nb.RayBundle(origins=g["origins"].to(DEV), directions=g["directions"].to(DEV), pixel_area=g["pixel_area"].to(DEV),
+                      times=g["times"].to(DEV), metadata={})
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    if mode == "train":  # replay the reference's per-ray flip draw
+        flip = g["train_ray_flip"].to(DEV)
+        orig = fld.hashgrid._apply_actors
+        fld.hashgrid._apply_actors = lambda *a, **k: orig(*a, ray_flip=flip, **k)
+    out = fld(rs)
+    ref_inside = (g[f"{mode}_grid_features"][:, 16:] == 0).all(dim=-1)
+    assert int(ref_inside.sum()) > 100
+    assert rel_err(out[nb.FieldHeadNames.FEATURE], g[f"{mode}_feature"]) <= 1e-3
+    assert float((out[nb.FieldHeadNames.ALPHA].detach().cpu() - g[f"{mode}_alpha"]).abs().max()) <= 1e-3
+    # the grid stage alone, through the reference-shaped API (GaussiansStd in, features + directions out)
+    gs = rs.frustums.get_fast_isotropic_gaussian(1)
+    if mode == "train":
+        fld.hashgrid._apply_actors = lambda *a, **k: orig(*a, ray_flip=flip, **k)
+    feats, dirs = fld.hashgrid(gs, rs.times, rs.frustums.directions)
+    assert torch.equal((feats[:, 16:] == 0).all(dim=-1).cpu(), ref_inside), "the same samples must be claimed by actors"
+    assert rel_err(feats, g[f"{mode}_grid_features"]) <= 1e-4
+    assert rel_err(dirs, g[f"{mode}_grid_directions"]) <= 1e-5
+    if mode == "train":
+        ((out[nb.FieldHeadNames.FEATURE] * g["train_gf"].to(DEV)).sum()
+         + (out[nb.FieldHeadNames.ALPHA] * g["train_ga"].to(DEV)).sum()).backward()
+        assert rel_err(fld.hashgrid.static_grid.hash_table.grad, g["train_d_static_table"]) <= 1e-3
+        for i in range(3):
+            got = fld.hashgrid.actor_grids[i].hash_table.grad
+            ref = g[f"train_d_actor_table{i}"]
+            if float(ref.abs().max()) > 0:
+                assert rel_err(got, ref) <= 1e-3, i
+        assert rel_err(fld.mlp_geo.layers[0].weight.grad, g["train_d_geo_w0"]) <= 1e-3
