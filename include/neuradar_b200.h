@@ -232,6 +232,20 @@ int nrb_accumulate_fwd(const float* weights, const float* values, int64_t N, int
 int nrb_accumulate_bwd(const float* weights, const float* values, const float* dout, int64_t N, int32_t S, int32_t C,
                        float* dweights, float* dvalues, nrb_stream_t stream);
 
+/* ---- per-ray training losses on the path's outputs ----
+ * MipNeRF-360 distortion loss (nerfstudio/model_components/losses.py:137-156, called on the final level at
+ * models/neurad.py via ray_samples.spacing bins): sbins [N,S+1] (row stride bin_stride floats), weights [N,S] ->
+ * loss_per_ray [N]; grad_factor [N,S] (may be NULL) = d loss_per_ray / d weights. */
+int nrb_distortion_loss(const float* sbins, int64_t bin_stride, const float* weights, int64_t N, int32_t S,
+                        float* loss_per_ray, float* grad_factor, nrb_stream_t stream);
+/* ZipNeRF anti-aliased interlevel loss of ONE proposal round (losses.py:620-705): the final level's spacing bins
+ * c [N,Sc+1] and weights w [N,Sc] (constants; the remaining accumulation is added to the last sample inside) are
+ * blurred with a box of half-width pulse_width and resampled at the proposal's bins cp [N,Sp+1]; wp [N,Sp] are the
+ * proposal's weights.  loss_per_ray [N]; grad_factor [N,Sp] (may be NULL) = d loss_per_ray / d wp. */
+int nrb_interlevel_loss(const float* c_bins, int64_t c_stride, const float* w, int32_t Sc, const float* cp_bins,
+                        int64_t cp_stride, const float* wp, int32_t Sp, float pulse_width, int64_t N,
+                        float* loss_per_ray, float* grad_factor, nrb_stream_t stream);
+
 /* ---- fused proposal round: NeuRADProposalField.get_density + RaySamples.get_weights
  * (fields/neurad_field.py:208-213, cameras/rays.py:188-210) in one kernel, one warp per ray:
  * gaussians -> contraction -> hash encode -> level weights -> Linear(L*F, 1, bias=False) -> trunc_exp -> weights.

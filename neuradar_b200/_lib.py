@@ -127,6 +127,8 @@ SIGNATURES = {
     "nrb_accumulate_fwd": [_P, _P, _I64, _I32, _I32, _P, _P],
     "nrb_accumulate_bwd": [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
     "nrb_alpha_composite_bwd": [_P, _P, C.POINTER(Intervals), _I64, _I32, _F, _I32, _P, _P, _P, _P, _P, _P, _P],
+    "nrb_distortion_loss": [_P, _I64, _P, _I64, _I32, _P, _P, _P],
+    "nrb_interlevel_loss": [_P, _I64, _P, _I32, _P, _I64, _P, _I32, _F, _I64, _P, _P, _P],
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
     "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P, _I64, _P],
 }

@@ -623,3 +623,62 @@ def field_forward_with_actors(p: FieldParams, actor_grids: Sequence[GridParams],
     sdf = sdf.view(n, s, 1)
     alpha = torch.sigmoid(-sdf * (p.beta.abs() + p.beta_min))
     return {"feature": feature.view(n, s, -1), "sdf": sdf, "alpha": alpha, "grid_features": feats, "directions": dirs}
+
+
+# --------------------------------------------------------------------------------------------
+# losses that run on the path's outputs every training step
+# --------------------------------------------------------------------------------------------
+def distortion_loss(sdist: Tensor, w: Tensor) -> Tensor:
+    """MipNeRF-360 distortion loss of the final level, mean over rays (model_components/losses.py:137-156).
+
+    sdist [N, S+1] spacing-domain bin edges, w [N, S] weights."""
+    ut = (sdist[..., 1:] + sdist[..., :-1]) / 2
+    dut = torch.abs(ut[..., :, None] - ut[..., None, :])
+    inter = torch.sum(w * torch.sum(w[..., None, :] * dut, dim=-1), dim=-1)
+    intra = torch.sum(w**2 * (sdist[..., 1:] - sdist[..., :-1]), dim=-1) / 3
+    return torch.mean(inter + intra)
+
+
+def _blur_stepfun(x: Tensor, y: Tensor, r: float) -> Tuple[Tensor, Tensor]:
+    """Convolve the step function (x, y) with a box of half-width r -> piecewise linear (losses.py:620-629)."""
+    xr, order = torch.sort(torch.cat([x - r, x + r], dim=-1))
+    zero = torch.zeros_like(y[..., :1])
+    y1 = (torch.cat([y, zero], dim=-1) - torch.cat([zero, y], dim=-1)) / (2 * r)
+    y2 = torch.cat([y1, -y1], dim=-1).take_along_dim(order[..., :-1], dim=-1)
+    yr = torch.cumsum((xr[..., 1:] - xr[..., :-1]) * torch.cumsum(y2, dim=-1), dim=-1).clamp_min(0)
+    return xr, torch.cat([torch.zeros_like(yr[..., :1]), yr], dim=-1)
+
+
+def _interp_quad(x: Tensor, xp: Tensor, fpdf: Tensor, fcdf: Tensor) -> Tensor:
+    """Piecewise-quadratic CDF of a piecewise-linear PDF evaluated at sorted queries (losses.py:632-645)."""
+    right = torch.searchsorted(xp, x)
+    left = (right - 1).clamp_min(0)
+    right = right.clamp_max(xp.shape[-1] - 1)
+    xp0, xp1 = xp.take_along_dim(left, dim=-1), xp.take_along_dim(right, dim=-1)
+    p0, p1 = fpdf.take_along_dim(left, dim=-1), fpdf.take_along_dim(right, dim=-1)
+    c0 = fcdf.take_along_dim(left, dim=-1)
+    off = torch.clip(torch.nan_to_num((x - xp0) / (xp1 - xp0), 0), 0, 1)
+    return c0 + (x - xp0) * (p0 + p1 * off + p0 * (1 - off)) * 0.5
+
+
+def zipnerf_interlevel_loss(c: Tensor, w: Tensor, proposals: Sequence[Tuple[Tensor, Tensor]],
+                            pulse_widths: Sequence[float] = (0.03, 0.003)) -> Tensor:
+    """Anti-aliased interlevel loss (losses.py:648-705).
+
+    c [N, S+1], w [N, S]: spacing bins and weights of the FINAL level (treated as constants);
+    proposals: (cp [N, Sp+1], wp [N, Sp]) per proposal round; gradients flow to wp only."""
+    c, w = c.detach(), w.detach()
+    w = torch.cat([w[..., :-1], w[..., -1:] + (1 - torch.sum(w, dim=-1, keepdim=True))], dim=-1)
+    w_norm = w / (c[..., 1:] - c[..., :-1])
+    loss = 0
+    for (cp, wp), r in zip(proposals, pulse_widths):
+        c_, w_ = _blur_stepfun(c, w_norm, r)
+        area = 0.5 * (w_[..., 1:] + w_[..., :-1]) * (c_[..., 1:] - c_[..., :-1])
+        cdf = torch.cat([torch.zeros_like(area[..., :1]), torch.cumsum(area, dim=-1)], dim=-1)
+        zero, one = torch.zeros_like(c_[..., :1]), torch.ones_like(c_[..., :1])
+        c_ = torch.cat([zero, c_, one], dim=-1)
+        w_ = torch.cat([zero, w_, zero], dim=-1)
+        cdf = torch.cat([zero, cdf, one], dim=-1)
+        w_s = torch.diff(_interp_quad(cp, c_, w_, cdf), dim=-1)
+        loss = loss + ((w_s - wp).clamp_min(0) ** 2 / (wp + 1e-5)).sum(dim=-1).mean()
+    return loss

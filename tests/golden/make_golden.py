@@ -438,7 +438,44 @@ def gen_actors():
     save("actors", **out)
 
 
+
+
+
+def gen_losses():
+    """zipnerf_interlevel_loss / distortion_loss (model_components/losses.py:137-156,648-705) on the golden path run."""
+    from nerfstudio.model_components.losses import distortion_loss, zipnerf_interlevel_loss
+
+    g = np.load(os.path.join(HERE, "path.npz"))
+    N = 64
+    rb = RayBundle(origins=torch.zeros((N, 3)), directions=torch.ones((N, 3)), pixel_area=torch.ones((N, 1)))
+    out = {}
+    rs_list, w_list = [], []
+    for i in range(3):
+        sb = torch.from_numpy(g[f"train_sbins{i}"])
+        if i == 2:
+            sb = sb[:, :-1]  # the sky sample is dropped before the losses (models/neuradar.py:515-516)
+        eb = sb.clone()
+        rs = rb.get_ray_samples(bin_starts=eb[:, :-1, None], bin_ends=eb[:, 1:, None], spacing_starts=sb[:, :-1, None],
+                                spacing_ends=sb[:, 1:, None])
+        rs_list.append(rs)
+        w = torch.from_numpy(g[f"train_prop_w{i}"] if i < 2 else g["train_weights"]).clone().requires_grad_(True)
+        w_list.append(w)
+        out[f"sbins{i}"], out[f"w{i}"] = sb, w
+    li = zipnerf_interlevel_loss(w_list, rs_list)
+    ld = distortion_loss(w_list, rs_list)
+    (li + ld).backward()
+    out["interlevel"], out["distortion"] = li, ld
+    for i in range(3):
+        out[f"dw{i}"] = w_list[i].grad
+    save("losses", **out)
+
+
 if __name__ == "__main__":
-    if "--actors-only" not in sys.argv:
+    if "--losses-only" in sys.argv:
+        gen_losses()
+    elif "--actors-only" in sys.argv:
+        gen_actors()
+    else:
         _main_all()
-    gen_actors()
+        gen_actors()
+        gen_losses()
