@@ -95,7 +95,7 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42):
+def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, regularisers: bool = False):
     """fwd+bwd of the reference algorithm (CPU oracle port, fp32 torch ops) on `num_rays` rays of the workload."""
     from oracle import neuradar_oracle as O
     from tests.parity_utils import scaled_pixel_area, synthetic_rays
@@ -128,7 +128,10 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42):
             t.grad = None
         jit = [torch.rand((num_rays, PROP_SAMPLES[0] + 1)), torch.rand((num_rays, 1)), torch.rand((num_rays, 1))]
         out = O.nff_forward(fld, [prop, prop], rays["origins"], rays["directions"], pa, rays["nears"], rays["fars"], cfg, jit)
-        O.bench_loss(out).backward()
+        loss = O.bench_loss(out)
+        if regularisers:
+            loss = loss + O.training_losses(out)
+        loss.backward()
 
     for _ in range(warmup):
         step()
@@ -144,7 +147,7 @@ def run_reference(args, rank):
         return
     sample = 4096
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, ms, cores = cpu_reference_run(sample, steps, warmup)
+    value, ms, cores = cpu_reference_run(sample, steps, warmup, regularisers=args.regularisers)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -197,6 +200,8 @@ def run_b200(args, rank, world, local_rank):
         arena.zero()
         out = model(bundle(src))
         loss = nb.bench_loss(out)
+        if args.regularisers:
+            loss = loss + nb.training_losses(out)
         loss.backward()
         arena.all_reduce()
         return loss
@@ -283,7 +288,8 @@ def run_b200(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD, "rays_per_gpu": n, "global_rays": total_rays,
                    "parallelism": f"ray-sharded dp{world}, one all-reduce of a {arena.nbytes / 2**20:.0f} MiB gradient arena",
                    "l2": "per-step working set (saved activations + gradient arena, > 1 GB) exceeds the 126 MB L2; "
-                         "no explicit flush", "optimizer": "not part of the path (SURVEY.md 8f next-2)"},
+                         "no explicit flush", "optimizer": "not part of the path (SURVEY.md 8f next-2)",
+                   "regularisers": bool(args.regularisers)},
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
         "gpu_launches": int(launches),
@@ -294,7 +300,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, cms, cores = cpu_reference_run(4096, 2, 1)
+            v, cms, cores = cpu_reference_run(4096, 2, 1, regularisers=args.regularisers)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "4096 of the 65536 rays per step, 2 timed fwd+bwd steps of the oracle"}
         print(json.dumps(line))
@@ -308,6 +314,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--regularisers", action="store_true",
+                    help="add the interlevel + distortion losses (SURVEY.md 8f next-1) to the step of both arms")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))

@@ -39,14 +39,16 @@ __global__ void __launch_bounds__(kLossWarps * 32) distortion_kernel(const float
   if (lane == 0) loss[n] = acc;
 }
 
-// inclusive scan over a shared array of `len` floats by one warp (in place)
+// Inclusive scan over a shared array of `len` floats by one warp (in place).  The running sum is carried in fp64 and
+// rounded to fp32 per element, which is what torch.cumsum does on the host (at::acc_type<float, false> is double):
+// the blurred histogram is a difference of large cancelling prefix sums, and an fp32 carry moves the loss by percents.
 __device__ __forceinline__ void warp_scan_inplace(float* a, int len, int lane) {
-  float carry = 0.0f;
+  double carry = 0.0;
   for (int base = 0; base < len; base += 32) {
     const int i = base + lane;
-    const float v = (i < len) ? a[i] : 0.0f;
-    const float incl = carry + warp_inclusive_sum(v, lane);
-    if (i < len) a[i] = incl;
+    const double v = (i < len) ? static_cast<double>(a[i]) : 0.0;
+    const double incl = carry + warp_inclusive_sum(v, lane);
+    if (i < len) a[i] = static_cast<float>(incl);
     carry = __shfl_sync(kFull, incl, 31);
   }
   __syncwarp();

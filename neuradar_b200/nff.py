@@ -156,3 +156,12 @@ def bench_loss(out: Dict[str, Tensor]) -> Tensor:
     for w in out["weights_list"][:-1]:
         loss = loss + w.pow(2).mean()
     return loss
+
+
+def training_losses(out: Dict[str, Tensor], interlevel_mult: float = 0.001, distortion_mult: float = 0.002) -> Tensor:
+    """The sampler regularisers NeuRadarModel.get_loss_dict adds every step (models/neurad.py:524-545; multipliers
+    :83-85): ZipNeRF interlevel loss of both proposal rounds + MipNeRF-360 distortion loss of the final level."""
+    from .losses import distortion_loss, zipnerf_interlevel_loss
+
+    wl, rl = out["weights_list"], out["ray_samples_list"]
+    return interlevel_mult * zipnerf_interlevel_loss(wl, rl) + distortion_mult * distortion_loss(wl, rl)

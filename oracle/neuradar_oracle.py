@@ -640,7 +640,10 @@ def distortion_loss(sdist: Tensor, w: Tensor) -> Tensor:
 
 
 def _blur_stepfun(x: Tensor, y: Tensor, r: float) -> Tuple[Tensor, Tensor]:
-    """Convolve the step function (x, y) with a box of half-width r -> piecewise linear (losses.py:620-629)."""
+    """Convolve the step function (x, y) with a box of half-width r -> piecewise linear (losses.py:620-629).
+
+    Note: on the host torch.cumsum carries its running sum in fp64 (rounded to fp32 per element); the two nested
+    prefix sums cancel heavily, so the CUDA kernel carries in fp64 too (csrc/losses.cu)."""
     xr, order = torch.sort(torch.cat([x - r, x + r], dim=-1))
     zero = torch.zeros_like(y[..., :1])
     y1 = (torch.cat([y, zero], dim=-1) - torch.cat([zero, y], dim=-1)) / (2 * r)
@@ -682,3 +685,11 @@ def zipnerf_interlevel_loss(c: Tensor, w: Tensor, proposals: Sequence[Tuple[Tens
         w_s = torch.diff(_interp_quad(cp, c_, w_, cdf), dim=-1)
         loss = loss + ((w_s - wp).clamp_min(0) ** 2 / (wp + 1e-5)).sum(dim=-1).mean()
     return loss
+
+
+def training_losses(out: PathOutputs, interlevel_mult: float = 0.001, distortion_mult: float = 0.002) -> Tensor:
+    """The two sampler regularisers of NeuRadarModel.get_loss_dict (models/neurad.py:524-545, defaults :83-85)."""
+    w_final = out.weights_list[-1][..., 0]
+    proposals = [(sb, w[..., 0]) for sb, w in zip(out.sbins_list[:-1], out.weights_list[:-1])]
+    inter = zipnerf_interlevel_loss(out.sbins_list[-1], w_final, proposals)
+    return interlevel_mult * inter + distortion_mult * distortion_loss(out.sbins_list[-1], w_final)

@@ -188,9 +188,11 @@ def rel_err(a: Tensor, b: Tensor) -> float:
 
 
 def run_path_parity(num_rays: int = 256, device: str = "cuda:0", seed: int = 3, train: bool = True,
-                    log2_main: int = 14, log2_prop: int = 14, tol: float = 1e-3) -> Dict[str, object]:
-    """Run the CUDA hot path and the CPU oracle on the same rays, parameters and jitter; compare everything."""
-    from neuradar_b200 import bench_loss
+                    log2_main: int = 14, log2_prop: int = 14, tol: float = 1e-3, with_losses: bool = False) -> Dict[str, object]:
+    """Run the CUDA hot path and the CPU oracle on the same rays, parameters and jitter; compare everything.
+    with_losses adds the interlevel + distortion regularisers (at 100x their default multipliers so that their
+    gradients are not hidden under the synthetic loss's)."""
+    from neuradar_b200 import bench_loss, training_losses
 
     S0, S1, S2 = 64, 48, 48
     model = build_hot_path(log2_main=log2_main, log2_prop=log2_prop, num_proposal_samples=(S0, S1), num_nerf_samples=S2,
@@ -221,8 +223,12 @@ def run_path_parity(num_rays: int = 256, device: str = "cuda:0", seed: int = 3, 
         for i in range(3):
             report[f"weights_{i}"] = rel_err(out["weights_list"][i], ref.weights_list[i])
         loss = bench_loss(out)
-        loss.backward()
         ref_loss = O.bench_loss(ref)
+        if with_losses:
+            reg, ref_reg = training_losses(out, 0.1, 0.2), O.training_losses(ref, 0.1, 0.2)
+            report["regularisers"] = abs(reg.item() - ref_reg.item()) / abs(ref_reg.item())
+            loss, ref_loss = loss + reg, ref_loss + ref_reg
+        loss.backward()
         ref_loss.backward()
         report["loss"] = abs(loss.item() - ref_loss.item()) / abs(ref_loss.item())
         leaves = named_leaves(fld, props)

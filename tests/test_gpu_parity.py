@@ -400,6 +400,12 @@ def test_whole_path_vs_oracle(nb, train):
     assert report["ok"], report
 
 
+def test_whole_path_with_regularisers_vs_oracle(nb):
+    """The step as the model trains it: path + interlevel + distortion losses, gradients of every parameter."""
+    report = run_path_parity(num_rays=384, device=DEV, seed=17, train=True, with_losses=True)
+    assert report["ok"], report
+
+
 @pytest.mark.parametrize("mode", ["train", "eval"])
 def test_whole_path_golden(nb, golden, mode):
     """The path on the reference's own outputs (tests/golden/path.npz, made by running the reference)."""
