@@ -175,7 +175,7 @@ inline int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
   // at most cap_mb per level; levels that already fill the table get `hashed` replicas of the hashed table itself
   static const double scale = env_or("NRB_BWD_SCALE", 4.0), cap_mb = env_or("NRB_BWD_CAP_MB", 32.0);
   static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 4.0));
-  static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 6.0));
+  static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 4.0));
   const int F = grid->features_per_level;
   const int64_t T = int64_t{1} << grid->log2_hashmap_size;
   const double table_rows = static_cast<double>(T);

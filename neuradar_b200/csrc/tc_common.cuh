@@ -404,5 +404,212 @@ __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
   return v[0];
 }
 
+
+// ---- column-split variants: a 128-row tile is handled by 128 * S threads; thread (h, r) owns the W = 32 / S columns
+// [h*W, (h+1)*W) of row r.  More warps per SM sub-partition hide the shuffle / shared-memory / mbarrier latencies that
+// dominate the one-thread-per-row kernels, and each thread's serial staging work shrinks by S.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// W (8, 16 or 32) accumulator columns of this thread's row, starting at column col0.
+template <int W>
+__device__ __forceinline__ void tmem_load_cols(uint32_t tmem_base, int warp, int col0, float (&v)[W]) {
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + static_cast<uint32_t>(col0);
+  if constexpr (W == 8) {
+    tmem_ld8(taddr, v);
+  } else {
+#pragma unroll
+    for (int c = 0; c < W / 16; ++c) {
+      float t[16];
+      tmem_ld16(taddr + c * 16, t);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[c * 16 + i] = t[i];
+    }
+  }
+  tmem_ld_wait();
+}
+
+// columns [col0, col0 + W) of one row of a canonical K-column tile, hi / lo halves
+template <int W>
+__device__ __forceinline__ void store_row_part_split(char* hi_tile, char* lo_tile, int row, int K, int col0,
+                                                     const float (&v)[W]) {
+#pragma unroll
+  for (int c = 0; c < W / 4; ++c) {
+    const float4 h = make_float4(tf32_hi(v[4 * c]), tf32_hi(v[4 * c + 1]), tf32_hi(v[4 * c + 2]), tf32_hi(v[4 * c + 3]));
+    const float4 l = make_float4(v[4 * c] - h.x, v[4 * c + 1] - h.y, v[4 * c + 2] - h.z, v[4 * c + 3] - h.w);
+    const uint32_t off = tile_offset(row, (col0 >> 2) + c, K);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+  }
+}
+
+// Transposed staging of W columns: lane `lane` of row-quarter `quarter` holds v[0..W) = columns [col0, col0+W) of row
+// 32 * quarter + lane; writes rows row_offset + [0, W) of the canonical [rows x 128] transposed tile (hi / lo).
+template <int W>
+__device__ __forceinline__ void store_part_transposed_split(char* hi_tile, char* lo_tile, int quarter, int lane,
+                                                            const float (&v)[W], int row_offset) {
+  const int i = lane & 3;
+  const int c4 = quarter * 8 + (lane >> 2);
+#pragma unroll
+  for (int g = 0; g < W / 4; ++g) {
+    float a0 = v[4 * g], a1 = v[4 * g + 1], a2 = v[4 * g + 2], a3 = v[4 * g + 3];
+    {
+      const bool odd = (i & 1) != 0;
+      const float s01 = odd ? a0 : a1, s23 = odd ? a2 : a3;
+      const float r01 = __shfl_xor_sync(kFull, s01, 1), r23 = __shfl_xor_sync(kFull, s23, 1);
+      if (odd) {
+        a0 = r01;
+        a2 = r23;
+      } else {
+        a1 = r01;
+        a3 = r23;
+      }
+    }
+    {
+      const bool up = (i & 2) != 0;
+      const float s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+      const float r0 = __shfl_xor_sync(kFull, s0, 2), r1 = __shfl_xor_sync(kFull, s1, 2);
+      if (up) {
+        a0 = r0;
+        a1 = r1;
+      } else {
+        a2 = r0;
+        a3 = r1;
+      }
+    }
+    const float4 h = make_float4(tf32_hi(a0), tf32_hi(a1), tf32_hi(a2), tf32_hi(a3));
+    const float4 l = make_float4(a0 - h.x, a1 - h.y, a2 - h.z, a3 - h.w);
+    const uint32_t off = tile_offset(row_offset + 4 * g + i, c4, kRows);
+    *reinterpret_cast<float4*>(hi_tile + off) = h;
+    *reinterpret_cast<float4*>(lo_tile + off) = l;
+  }
+}
+
+// Coalesced I/O of columns [col0, col0 + W) of 32 consecutive rows of a row-major [M, 32] matrix by one warp:
+// W / 4 lanes per row, W / 4 loads per lane, redistributed through a 32 * W * 4 byte bounce buffer whose 16-byte
+// chunks are XOR-swizzled so that both the chunk-major and the row-major phase are bank-conflict free.
+template <int W>
+__device__ __forceinline__ int bounce_swizzle(int row) {
+  constexpr int CPR = W / 4, RP = 8 / CPR;  // chunks per row, rows per 128 bytes
+  return (row / RP) % CPR;
+}
+
+template <int W>
+__device__ __forceinline__ void warp_load_part_coalesced(const float* __restrict__ g, int64_t row_base, int64_t M, int col0,
+                                                         int lane, float4 (&pf)[W / 4]) {
+  constexpr int CPR = W / 4, RPI = 32 / CPR;
+#pragma unroll
+  for (int q = 0; q < CPR; ++q) {
+    const int64_t r = min(row_base + q * RPI + lane / CPR, M - 1);
+    pf[q] = __ldg(reinterpret_cast<const float4*>(g + r * 32 + col0) + (lane % CPR));
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void warp_bounce_part_to_rows(char* bounce, int lane, const float4 (&pf)[W / 4], float (&v)[W]) {
+  constexpr int CPR = W / 4, RPI = 32 / CPR;
+#pragma unroll
+  for (int q = 0; q < CPR; ++q) {
+    const int r = q * RPI + lane / CPR, cc = lane % CPR;
+    *reinterpret_cast<float4*>(bounce + r * (W * 4) + ((cc ^ bounce_swizzle<W>(r)) << 4)) = pf[q];
+  }
+  __syncwarp();
+#pragma unroll
+  for (int cc = 0; cc < CPR; ++cc) {
+    const float4 t = *reinterpret_cast<const float4*>(bounce + lane * (W * 4) + ((cc ^ bounce_swizzle<W>(lane)) << 4));
+    v[4 * cc] = t.x;
+    v[4 * cc + 1] = t.y;
+    v[4 * cc + 2] = t.z;
+    v[4 * cc + 3] = t.w;
+  }
+  __syncwarp();
+}
+
+template <int W>
+__device__ __forceinline__ void warp_store_part_coalesced(float* __restrict__ g, int64_t row_base, int64_t M, int col0,
+                                                          char* bounce, int lane, const float (&v)[W]) {
+  constexpr int CPR = W / 4, RPI = 32 / CPR;
+#pragma unroll
+  for (int cc = 0; cc < CPR; ++cc)
+    *reinterpret_cast<float4*>(bounce + lane * (W * 4) + ((cc ^ bounce_swizzle<W>(lane)) << 4)) =
+        make_float4(v[4 * cc], v[4 * cc + 1], v[4 * cc + 2], v[4 * cc + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < CPR; ++q) {
+    const int r = q * RPI + lane / CPR, cc = lane % CPR;
+    const float4 t = *reinterpret_cast<const float4*>(bounce + r * (W * 4) + ((cc ^ bounce_swizzle<W>(r)) << 4));
+    if (row_base + r < M) reinterpret_cast<float4*>(g + (row_base + r) * 32 + col0)[cc] = t;
+  }
+  __syncwarp();
+}
+
+
+// ---- A operand from tensor memory (".ts" form): D[128, n] (+)= A[128, K] * B[n, K]^T where row r of A sits in TMEM lane
+// r, one 32-bit column per K element.  Threads write their own rows with tcgen05.st; no shared-memory staging or
+// shared-memory operand fetch for A.
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+               "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+               "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+               "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// columns [col, col + W) of this thread's row, as tf32 hi / lo halves at hi_col / lo_col
+template <int W>
+__device__ __forceinline__ void tmem_store_row_split(uint32_t tmem_base, int warp, int hi_col, int lo_col, int col,
+                                                     const float (&v)[W]) {
+  const uint32_t lane_base = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+#pragma unroll
+  for (int c = 0; c < W / 8; ++c) {
+    float hi[8], lo[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      hi[i] = tf32_hi(v[8 * c + i]);
+      lo[i] = v[8 * c + i] - hi[i];
+    }
+    tmem_st8(lane_base + static_cast<uint32_t>(hi_col + col + 8 * c), hi);
+    tmem_st8(lane_base + static_cast<uint32_t>(lo_col + col + 8 * c), lo);
+  }
+  tmem_st_wait();
+}
+
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                            bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+
+// 3xTF32 chain with A (hi / lo) in TMEM columns and B (hi / lo) K-major canonical tiles of b_cols columns.  One thread.
+// Back-to-back tcgen05.mma into the SAME accumulator serialise on its read-modify-write (measured ~55 cycles per
+// instruction for these small shapes, whatever the operand source), so every K step gets its own accumulator
+// (d_tmem + k * d_stride columns, chains of three) and the consumer adds the k_red / 8 partial results.
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, int d_stride, int n, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
+                                              uint32_t b_hi, uint32_t b_lo, int b_cols, int k_red) {
+  const uint32_t idesc = make_idesc_m(128, n, 0, 0);
+  const uint32_t b_sbo = static_cast<uint32_t>(b_cols / 4) * 128u;
+  const uint64_t bh = make_desc(b_hi, 128, b_sbo), bl = make_desc(b_lo, 128, b_sbo);
+  const int steps = k_red / 8;
+#pragma unroll 4
+  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_lo_tmem + 8 * k, bh + 16 * k, idesc, false);
+#pragma unroll 4
+  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_hi_tmem + 8 * k, bl + 16 * k, idesc, true);
+#pragma unroll 4
+  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_hi_tmem + 8 * k, bh + 16 * k, idesc, true);
+}
+
 }  // namespace tc
 }  // namespace nrb

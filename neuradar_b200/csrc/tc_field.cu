@@ -12,6 +12,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <cuda_bf16.h>
+
 #include "tc_common.cuh"
 
 namespace nrb {
@@ -568,6 +570,486 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
   if (warp == 0) tmem_free<kBwdTmemCols>(tmem_base);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Column-split backward kernel (the one that runs; field_mlp_bwd_kernel above is kept as NRB_FIELD_BWD_SPLIT=1).
+// Same mathematics and the same two GEMM chains per layer, re-organised around what the ncu / clock64 traces showed to
+// bound the one-thread-per-row kernel: shared-memory bandwidth (operand staging + the tensor core re-reading both
+// operands for every K = 8 instruction) and a fully serial stage -> issue -> wait chain with one warp per scheduler.
+//   * a tile is worked on by 128 * S threads (S = 2 or 4): thread (h, r) owns columns [h*W, (h+1)*W), W = 32 / S, of
+//     row r; one extra warp only issues tcgen05.mma (workers signal it through named barrier 1, it answers through
+//     mbarriers), so the workers never stall behind the issue of the long weight-gradient chain;
+//   * the weight-gradient GEMM [dW_l | db_l] += delta^T [input | 1] runs as kind::f16 on bf16 pairs: every value is
+//     split into hi = top 16 bits and mid = bf16(x - hi), products hi*hi + hi*mid + mid*hi (relative error ~2^-16 per
+//     product, averaged down further by the reduction over all samples - the tolerance is 1e-3).  K = 16 per
+//     instruction and 2-byte elements halve both the staging bytes and the operand bytes the tensor core reads, and
+//     the smaller tiles leave room to double-buffer delta^T / input^T, so the chain of layer l overlaps the staging
+//     and the data-gradient GEMM of layer l-1.  hi and mid tiles of delta^T are adjacent and read as ONE 128-row A
+//     operand (two instructions per K step give all four partial products);
+//   * the data-gradient chain (the critical path, errors compound through five layers) stays 3xTF32, with its A operand
+//     (this thread's delta row, hi / lo) written straight to tensor memory with tcgen05.st and read from there by the
+//     ".ts" form of tcgen05.mma: no shared-memory staging or operand fetch for it;
+//   * bias gradients come from the tensor cores: the input^T operand carries one extra row of ones (N = 40 / 56), so
+//     column 32 (48) of every dW accumulator is sum_s delta = db;
+//   * layer 1 (33 outputs = [sdf | emb]) feeds only the 32 emb columns to the data-gradient GEMM; the sdf row of W1 is
+//     a rank-1 update on the CUDA cores.  Every delta tile is then 32 columns wide and chunk-aligned;
+//   * global loads that are consumed layers later (x rows, SH basis, sdf / alpha terms, next tile's d feature rows) are
+//     issued at the top of the tile.
+// TMEM map (512 columns): four 48-column data-gradient accumulators (one per K step), the five weight-gradient
+// accumulators, and the data-gradient GEMM's A operand (delta as tf32 hi / lo).
+constexpr int kBwd2TmemCols = 512;
+constexpr int kDinStride = 48;
+__device__ constexpr int kDw2Col[5] = {192, 240, 288, 352, 400};  // TMEM column of each layer's dW (+db) accumulator
+__device__ constexpr int kDw2N[5] = {48, 48, 64, 48, 48};         // N of the weight-gradient GEMM (inputs + ones + pad)
+constexpr int kBwd2AHi = 448, kBwd2ALo = 480;
+constexpr int kDt16Bytes = 64 * kRows * 2;  // delta^T as bf16: 64 rows (33 used) x 128 samples
+constexpr int kAt16Bytes = 64 * kRows * 2;  // [input | ones]^T as bf16: 64 rows (<= 49 used) x 128 samples
+
+struct FieldBwd2Smem {
+  static constexpr int w1row0 = field_w_hi(5);           // sdf row of W1, 32 floats
+  static constexpr int dt = w1row0 + 128;                // [2 buffers][hi, mid] delta^T
+  static constexpr int at = dt + 4 * kDt16Bytes;         // [2 buffers][hi, mid] [input | ones]^T
+  static constexpr int bounce = at + 4 * kAt16Bytes;     // 16 KB of per-warp bounce buffers
+  static constexpr int mbar = bounce + 16384;            // data, dw[0], dw[1]
+  static constexpr int tmem = mbar + 32;
+  static constexpr int total = tmem + 16;
+};
+
+// byte offset of (row, 8-sample chunk) in a canonical K-major bf16 tile with 128 columns
+__device__ __forceinline__ uint32_t tile16_offset(int row, int chunk8) {
+  return static_cast<uint32_t>((row >> 3) * 2048 + chunk8 * 128 + (row & 7) * 16);
+}
+
+// four consecutive K elements -> packed bf16 hi (truncated) and mid (rounded residual)
+__device__ __forceinline__ void split_bf16x4(float a0, float a1, float a2, float a3, uint2& hi, uint2& mid) {
+  const uint32_t b0 = __float_as_uint(a0), b1 = __float_as_uint(a1), b2 = __float_as_uint(a2), b3 = __float_as_uint(a3);
+  hi.x = __byte_perm(b0, b1, 0x7632);
+  hi.y = __byte_perm(b2, b3, 0x7632);
+  const float r0 = a0 - __uint_as_float(b0 & 0xFFFF0000u), r1 = a1 - __uint_as_float(b1 & 0xFFFF0000u);
+  const float r2 = a2 - __uint_as_float(b2 & 0xFFFF0000u), r3 = a3 - __uint_as_float(b3 & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.x) : "f"(r1), "f"(r0));
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(mid.y) : "f"(r3), "f"(r2));
+}
+
+// (row, samples 4*c4 .. 4*c4+3) of a bf16 hi / mid tile pair
+__device__ __forceinline__ void store_bf16x4(char* hi_tile, char* mid_tile, int row, int c4, float a0, float a1, float a2,
+                                             float a3) {
+  uint2 hi, mid;
+  split_bf16x4(a0, a1, a2, a3, hi, mid);
+  const uint32_t off = tile16_offset(row, c4 >> 1) + (c4 & 1) * 8;
+  *reinterpret_cast<uint2*>(hi_tile + off) = hi;
+  *reinterpret_cast<uint2*>(mid_tile + off) = mid;
+}
+
+// Transposed bf16 staging of W columns held row-per-lane (see store_part_transposed_split).
+template <int W>
+__device__ __forceinline__ void store_part_transposed_bf16(char* hi_tile, char* mid_tile, int quarter, int lane,
+                                                           const float (&v)[W], int row_offset) {
+  const int i = lane & 3;
+  const int c4 = quarter * 8 + (lane >> 2);
+#pragma unroll
+  for (int g = 0; g < W / 4; ++g) {
+    float a0 = v[4 * g], a1 = v[4 * g + 1], a2 = v[4 * g + 2], a3 = v[4 * g + 3];
+    {
+      const bool odd = (i & 1) != 0;
+      const float s01 = odd ? a0 : a1, s23 = odd ? a2 : a3;
+      const float r01 = __shfl_xor_sync(kFull, s01, 1), r23 = __shfl_xor_sync(kFull, s23, 1);
+      if (odd) {
+        a0 = r01;
+        a2 = r23;
+      } else {
+        a1 = r01;
+        a3 = r23;
+      }
+    }
+    {
+      const bool up = (i & 2) != 0;
+      const float s0 = up ? a0 : a2, s1 = up ? a1 : a3;
+      const float r0 = __shfl_xor_sync(kFull, s0, 2), r1 = __shfl_xor_sync(kFull, s1, 2);
+      if (up) {
+        a0 = r0;
+        a1 = r1;
+      } else {
+        a2 = r0;
+        a3 = r1;
+      }
+    }
+    store_bf16x4(hi_tile, mid_tile, row_offset + 4 * g + i, c4, a0, a1, a2, a3);
+  }
+}
+
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(static_cast<uint32_t>(accumulate))
+      : "memory");
+}
+
+// D[128, n] (+)= [A_hi; A_mid][128, 128] * B^T over bf16 hi / mid pairs: the hi and mid tiles of A (64 rows each) are
+// adjacent in shared memory and form ONE 128-row operand, so two instructions per K step (x B_hi, x B_mid) produce
+// all four partial products; rows 0..63 of D hold hi * (hi + mid), rows 64..127 mid * (hi + mid).  One thread.
+__device__ __forceinline__ void issue_gemm_bf16_stacked(uint32_t d_tmem, int n, uint32_t a_stacked, uint32_t b_hi,
+                                                        uint32_t b_mid, bool accumulate_first) {
+  // kind::f16 instruction descriptor: fp32 accumulate, bf16 x bf16, both K-major, M = 128
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | ((128u >> 4) << 24);
+  uint64_t a = make_desc(a_stacked, 128, 2048);
+  uint64_t bh = make_desc(b_hi, 128, 2048), bm = make_desc(b_mid, 128, 2048);
+  bool acc = accumulate_first;
+#pragma unroll
+  for (int k = 0; k < kRows / 16; ++k) {  // K = 16 per instruction = two 16-byte chunks = 256 bytes
+    mma_bf16(d_tmem, a, bm, idesc, acc);
+    mma_bf16(d_tmem, a, bh, idesc, true);
+    acc = true;
+    a += 16;
+    bh += 16;
+    bm += 16;
+  }
+}
+
+// Debug only (NRB_FIELD_BWD_DEBUG bit 2): thread 0 of CTA 0 stamps clock64() at the phase boundaries of its tiles.
+__device__ long long g_bwd_trace[2048];
+#define NRB_TRACE()                                                                                      \
+  do {                                                                                                   \
+    if ((dbg & 4) && t == 0 && blockIdx.x == 0 && trace_n < 1024) g_bwd_trace[trace_n++] = clock64();    \
+  } while (0)
+
+template <int S>
+__global__ void __launch_bounds__(kRows * S + 32, 1) field_mlp_bwd_split_kernel(const __grid_constant__ FieldParams prm,
+                                                                                const __grid_constant__ FieldBwdIn in,
+                                                                                const __grid_constant__ FieldBwdOut out,
+                                                                                int samples_per_ray, int64_t M, int dbg) {
+  constexpr int W = 32 / S, T = kRows * S, NPF = 1024 / T, NSH = (16 * 32 + T - 1) / T;
+  extern __shared__ __align__(128) char smem[];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int h = warp >> 2, quarter = warp & 3, r = t & (kRows - 1), col0 = h * W;
+  const bool issuer = warp == 4 * S;  // the extra warp
+  auto dt_hi = [&](int b) { return smem + FieldBwd2Smem::dt + (2 * b) * kDt16Bytes; };
+  auto dt_mid = [&](int b) { return smem + FieldBwd2Smem::dt + (2 * b + 1) * kDt16Bytes; };
+  auto at_hi = [&](int b) { return smem + FieldBwd2Smem::at + (2 * b) * kAt16Bytes; };
+  auto at_mid = [&](int b) { return smem + FieldBwd2Smem::at + (2 * b + 1) * kAt16Bytes; };
+  float* w1row0 = reinterpret_cast<float*>(smem + FieldBwd2Smem::w1row0);
+  uint64_t* mbar_data = reinterpret_cast<uint64_t*>(smem + FieldBwd2Smem::mbar);
+  uint64_t* mbar_dw = mbar_data + 1;  // [2], one per operand buffer
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldBwd2Smem::tmem);
+  char* bounce = smem + FieldBwd2Smem::bounce + (warp & (4 * S - 1)) * (32 * W * 4);
+
+  // W_l^T as the B operand of the data-gradient GEMM; layer 1 without its sdf row (rank-1 term below)
+  stage_weight_transposed_split(prm.w[0], 32, 32, 32, smem + field_w_hi(0), smem + field_w_lo(0));
+  stage_weight_transposed_split(prm.w[1] + 32, 32, 32, 32, smem + field_w_hi(1), smem + field_w_lo(1));
+  stage_weight_transposed_split(prm.w[2], 32, 32, 48, smem + field_w_hi(2), smem + field_w_lo(2));
+  stage_weight_transposed_split(prm.w[3], 32, 32, 32, smem + field_w_hi(3), smem + field_w_lo(3));
+  stage_weight_transposed_split(prm.w[4], 32, 32, 32, smem + field_w_hi(4), smem + field_w_lo(4));
+  if (t < 32) w1row0[t] = __ldg(prm.w[1] + t);
+  // operand buffers start as zeros (delta^T rows 32..63 and the padding rows of input^T stay zero / finite)
+  for (int e = t; e < (4 * kDt16Bytes + 4 * kAt16Bytes) / 16; e += T + 32)
+    reinterpret_cast<uint4*>(smem + FieldBwd2Smem::dt)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  // [ones, 0 x 7] rows of the input^T operand: rows 32..39 (layers with 32 inputs) and 48..55 (layer 2)
+  auto write_ones_rows = [&](int b, int row_base, int stride) {
+    for (int e = t; e < 8 * 16; e += stride) {
+      const uint32_t v = (e & 7) == 0 ? 0x3F803F80u : 0u;  // bf16 1.0 pairs
+      const uint32_t off = tile16_offset(row_base + (e & 7), e >> 3);
+      *reinterpret_cast<uint4*>(at_hi(b) + off) = make_uint4(v, v, v, v);
+      *reinterpret_cast<uint4*>(at_mid(b) + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  for (int b = 0; b < 2; ++b) {
+    write_ones_rows(b, 32, T + 32);
+    write_ones_rows(b, 48, T + 32);
+  }
+  if (warp == 0) tmem_alloc<kBwd2TmemCols>(tmem_slot);
+  if (t == 0) {
+    mbar_init(mbar_data, 1);
+    mbar_init(mbar_dw, 1);
+    mbar_init(mbar_dw + 1, 1);
+  }
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t tiles = (M + kRows - 1) / kRows;
+  const bool any = static_cast<int64_t>(blockIdx.x) < tiles;
+
+  if (issuer) {
+    // ---- the issuing warp: per layer wait for the workers' operands, then dIn chain (committed first: the workers
+    // wait for it) and the weight-gradient chain on this layer's operand buffer
+    bool first = true;
+    int it = 0;
+    int itrace = 1024;
+#define NRB_ITRACE()                                                                                   \
+  do {                                                                                                 \
+    if ((dbg & 4) && blockIdx.x == 0 && itrace < 2048) g_bwd_trace[itrace++] = clock64();              \
+  } while (0)
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+#pragma unroll 1
+      for (int l = 4; l >= 0; --l, ++it) {
+        const int b = it & 1;
+        asm volatile("bar.sync 1, %0;" ::"n"(T + 32) : "memory");
+        if (elect_one()) {
+          NRB_ITRACE();  // 0: all workers arrived
+          fence_after_sync();
+          if (!(dbg & 2))
+            issue_gemm_ts(tmem_base, kDinStride, kK[l], tmem_base + kBwd2AHi, tmem_base + kBwd2ALo,
+                          smem_u32(smem + field_w_hi(l)), smem_u32(smem + field_w_lo(l)), 32, 32);
+          mma_commit(mbar_data);
+          NRB_ITRACE();  // 1: dIn chain issued
+          if (!(dbg & 1))
+            issue_gemm_bf16_stacked(tmem_base + kDw2Col[l], kDw2N[l], smem_u32(dt_hi(b)), smem_u32(at_hi(b)),
+                                    smem_u32(at_mid(b)), !first);
+          mma_commit(mbar_dw + b);
+          NRB_ITRACE();  // 2: dW chain issued
+        }
+        __syncwarp();
+      }
+      first = false;
+    }
+  } else {
+    // ---- workers
+    const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
+    uint32_t phase_data = 0, phase_dw = 0, dw_pending = 0;  // bit b: operand buffer b
+    int it = 0;
+    float dbeta_acc = 0.0f;
+    int trace_n = 0;
+    // operands staged + this thread's TMEM reads complete -> arrive on the issuer's barrier
+    auto signal_issuer = [&](int b) {
+      fence_async_smem();
+      fence_before_sync();
+      asm volatile("bar.arrive 1, %0;" ::"n"(T + 32) : "memory");
+      dw_pending |= 1u << b;
+    };
+    auto wait_data = [&]() {
+      mbar_wait(mbar_data, phase_data);
+      phase_data ^= 1;
+      fence_after_sync();
+    };
+    auto wait_dw = [&](int b) {  // the chain that last read operand buffer b
+      if ((dw_pending >> b) & 1u) {
+        mbar_wait(mbar_dw + b, (phase_dw >> b) & 1u);
+        phase_dw ^= 1u << b;
+        dw_pending &= ~(1u << b);
+      }
+    };
+    auto prefetch_act = [&](const float* __restrict__ fm, int64_t row0, float4 (&pf)[NPF]) {
+#pragma unroll
+      for (int q = 0; q < NPF; ++q) {
+        const int e = t + q * T;
+        const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        pf[q] = __ldg(reinterpret_cast<const float4*>(fm + j * in.ld + row0 + 4 * c));
+      }
+    };
+    auto commit_act = [&](int b, const float4 (&pf)[NPF]) {  // rows 0..31 of input^T
+#pragma unroll
+      for (int q = 0; q < NPF; ++q) {
+        const int e = t + q * T;
+        const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        store_bf16x4(at_hi(b), at_mid(b), j, c, pf[q].x, pf[q].y, pf[q].z, pf[q].w);
+      }
+    };
+    auto stage_delta = [&](int b, const float (&v)[W]) {
+      tmem_store_row_split<W>(tmem_base, warp, kBwd2AHi, kBwd2ALo, col0, v);
+      store_part_transposed_bf16<W>(dt_hi(b), dt_mid(b), quarter, lane, v, col0);
+    };
+    auto load_din = [&](float (&v)[W]) {  // sum of the per-K-step partial accumulators
+      tmem_load_cols<W>(tmem_base, warp, col0, v);
+#pragma unroll
+      for (int k = 1; k < 4; ++k) {
+        float p[W];
+        tmem_load_cols<W>(tmem_base, warp, k * kDinStride + col0, p);
+#pragma unroll
+        for (int j = 0; j < W; ++j) v[j] += p[j];
+      }
+    };
+    auto apply_mask = [&](uint32_t m, float (&v)[W]) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = ((m >> (col0 + j)) & 1u) ? v[j] : 0.0f;
+    };
+
+    const int64_t last_ray = (M - 1) / samples_per_ray;
+    float4 pfa[NPF], pfb[NPF];  // two prefetch sets: every activation tile is requested two layers before its use
+    float4 df[W / 4];  // this thread's share of the tile's d feature rows, loaded one tile ahead
+    if (any) {
+      prefetch_act(in.g2, static_cast<int64_t>(blockIdx.x) * kRows, pfa);
+      warp_load_part_coalesced<W>(in.dfeature, static_cast<int64_t>(blockIdx.x) * kRows + quarter * 32, M, col0, lane, df);
+    }
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int64_t row0 = tile * kRows;
+      const int64_t row = row0 + r;
+      const bool ok = row < M;
+      const uint32_t m_h1 = __ldg(in.masks + row), m_g1 = __ldg(in.masks + in.ld + row), m_g2 = __ldg(in.masks + 2 * in.ld + row);
+      float delta[W], demb[W];
+      NRB_TRACE();  // 0: tile start
+      prefetch_act(in.g1, row0, pfb);
+      warp_bounce_part_to_rows<W>(bounce, lane, df, delta);
+      // loads consumed layers later are issued now: x rows (layer 0), SH basis (layer 2), sdf / alpha terms (layer 1)
+      float4 xpf[W / 4];
+      warp_load_part_coalesced<W>(in.x, row0 + quarter * 32, M, col0, lane, xpf);
+      float shv[NSH][4];
+#pragma unroll
+      for (int q = 0; q < NSH; ++q) {
+        const int e = t + q * T;
+        const int k = (e & 7) + 8 * ((e >> 8) & 1), c = (e >> 3) & 31;
+        const int64_t ray0 = (row0 + 4 * c) / samples_per_ray;
+        const int rem = static_cast<int>((row0 + 4 * c) - ray0 * samples_per_ray);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int64_t ray = min(ray0 + (rem + i) / samples_per_ray, last_ray);
+          shv[q][i] = __ldg(in.sh + ray * 16 + k);
+        }
+      }
+      const int64_t rc = ok ? row : (M - 1);
+      const float a_v = __ldg(in.alpha + rc), sd_v = __ldg(in.sdf + rc);
+      const float da_v = in.dalpha != nullptr ? __ldg(in.dalpha + rc) : 0.0f;
+      const float ds_v = in.dsdf != nullptr ? __ldg(in.dsdf + rc) : 0.0f;
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        delta[j] = ok ? delta[j] : 0.0f;
+        demb[j] = delta[j];  // residual branch
+      }
+      NRB_TRACE();  // 1
+      // ---- layer 4 (mlp_feature.layers.2): delta = d feature, input g2
+      int b = it & 1;
+      wait_dw(b);
+      NRB_TRACE();  // 2
+      stage_delta(b, delta);
+      commit_act(b, pfa);
+      write_ones_rows(b, 32, T);
+      NRB_TRACE();  // 3
+      signal_issuer(b);
+      ++it;
+      prefetch_act(in.emb, row0, pfa);
+      wait_data();
+      NRB_TRACE();  // 4
+      load_din(delta);
+      apply_mask(m_g2, delta);
+      // ---- layer 3 (mlp_feature.layers.1): input g1
+      b = it & 1;
+      wait_dw(b);
+      NRB_TRACE();  // 5
+      stage_delta(b, delta);
+      commit_act(b, pfb);
+      write_ones_rows(b, 32, T);
+      NRB_TRACE();  // 6
+      signal_issuer(b);
+      ++it;
+      prefetch_act(in.h1, row0, pfb);
+      wait_data();
+      NRB_TRACE();  // 7
+      load_din(delta);
+      apply_mask(m_g1, delta);
+      // ---- layer 2 (mlp_feature.layers.0): input [emb | sh | 1]
+      b = it & 1;
+      wait_dw(b);
+      NRB_TRACE();  // 8
+      stage_delta(b, delta);
+      commit_act(b, pfa);
+#pragma unroll
+      for (int q = 0; q < NSH; ++q) {  // rows 32..47 of the input^T tile: the ray's SH basis
+        const int e = t + q * T;
+        if (e < 16 * 32) {
+          const int k = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+          store_bf16x4(at_hi(b), at_mid(b), 32 + k, c, shv[q][0], shv[q][1], shv[q][2], shv[q][3]);
+        }
+      }
+      NRB_TRACE();  // 9
+      signal_issuer(b);
+      ++it;
+      {
+        const int64_t ntile = tile + gridDim.x;
+        if (ntile < tiles) {
+          prefetch_act(in.g2, ntile * kRows, pfa);
+          warp_load_part_coalesced<W>(in.dfeature, ntile * kRows + quarter * 32, M, col0, lane, df);
+        }
+      }
+      wait_data();
+      NRB_TRACE();  // 10
+      load_din(delta);  // the SH part of the input carries no gradient
+#pragma unroll
+      for (int j = 0; j < W; ++j) demb[j] += delta[j];
+      // ---- layer 1 (mlp_geo.layers.1): delta = [d sdf | d emb]; input h1
+      float dsdf_v = 0.0f;
+      if (ok) {
+        const float sg = a_v * (1.0f - a_v);
+        dsdf_v = ds_v - da_v * beta * sg;
+        if (h == 0) dbeta_acc -= da_v * sd_v * sg;
+      }
+      b = it & 1;
+      wait_dw(b);
+      NRB_TRACE();  // 11
+      stage_delta(b, demb);  // accumulator rows 0..31 <-> W1 rows 1..32
+      if (h == 0) {          // accumulator row 32 <-> W1 row 0 (sdf)
+        const uint32_t hb = __float_as_uint(dsdf_v) & 0xFFFF0000u;
+        const __nv_bfloat16 mid = __float2bfloat16_rn(dsdf_v - __uint_as_float(hb));
+        const uint32_t off = tile16_offset(32, r >> 3) + (r & 7) * 2;
+        *reinterpret_cast<uint16_t*>(dt_hi(b) + off) = static_cast<uint16_t>(hb >> 16);
+        *reinterpret_cast<__nv_bfloat16*>(dt_mid(b) + off) = mid;
+      }
+      commit_act(b, pfb);
+      write_ones_rows(b, 32, T);
+      NRB_TRACE();  // 12
+      signal_issuer(b);
+      ++it;
+      float xrow[W];
+      warp_bounce_part_to_rows<W>(bounce, lane, xpf, xrow);
+      wait_data();
+      NRB_TRACE();  // 13
+      load_din(delta);
+#pragma unroll
+      for (int j = 0; j < W; ++j) delta[j] = fmaf(dsdf_v, w1row0[col0 + j], delta[j]);
+      apply_mask(m_h1, delta);
+      // ---- layer 0 (mlp_geo.layers.0): input x (row-major in memory: transposed through registers)
+      b = it & 1;
+      wait_dw(b);
+      NRB_TRACE();  // 14
+      stage_delta(b, delta);
+      store_part_transposed_bf16<W>(at_hi(b), at_mid(b), quarter, lane, xrow, col0);
+      write_ones_rows(b, 32, T);
+      NRB_TRACE();  // 15
+      signal_issuer(b);
+      ++it;
+      wait_data();
+      NRB_TRACE();  // 16
+      if (out.dx != nullptr) {
+        load_din(delta);
+        warp_store_part_coalesced<W>(out.dx, row0 + quarter * 32, M, col0, bounce, lane, delta);
+      }
+      NRB_TRACE();  // 17
+    }
+    wait_dw(0);
+    wait_dw(1);
+    const float sb = warp_sum(dbeta_acc);
+    if (any && h == 0 && lane == 0 && out.dbeta != nullptr) atomicAdd(out.dbeta, sb);
+  }
+  // ---- flush: weight and bias gradients from TMEM
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (any && h == 0) {
+    const int ar = r & 63;  // rows 0..63: hi part, 64..127: mid part of the same weight-gradient row
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      float acc[64];
+      tmem_load_row<64>(tmem_base, warp, kDw2Col[l], acc);
+      const int wrow = (l == 1) ? (ar == 32 ? 0 : ar + 1) : ar;  // row of the weight matrix
+      if (wrow < kOut[l] && ar <= 32) {
+        if (out.dw[l] != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 48; ++k)
+            if (k < kK[l]) atomicAdd(out.dw[l] + wrow * kK[l] + k, acc[k]);
+        }
+        if (out.db[l] != nullptr) atomicAdd(out.db[l] + wrow, l == 2 ? acc[48] : acc[32]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<kBwd2TmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Generic probe of descriptor conventions: P and Q are [128,32] row-major host-provided matrices staged as canonical
 // tiles; one chain of `ksteps` tf32 MMAs is issued with caller-chosen majors, M, N, LBO/SBO and per-step address
 // advances; the [128 lanes][32 columns] accumulator block is dumped.
@@ -790,7 +1272,24 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
   static const int dbg = std::getenv("NRB_FIELD_BWD_DEBUG") ? std::atoi(std::getenv("NRB_FIELD_BWD_DEBUG")) : 0;
+  // threads per row: 1 = the one-thread-per-row kernel, 2 / 4 = the column-split kernel
+  static const int split = std::getenv("NRB_FIELD_BWD_SPLIT") ? std::atoi(std::getenv("NRB_FIELD_BWD_SPLIT")) : 4;
+  if (split == 2 || split == 4) {
+    auto kern = split == 2 ? field_mlp_bwd_split_kernel<2> : field_mlp_bwd_split_kernel<4>;
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwd2Smem::total);
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    kern<<<grid, tc::kRows * split + 32, FieldBwd2Smem::total, static_cast<cudaStream_t>(stream)>>>(to_params(p), bi, bo,
+                                                                                                   samples_per_ray, M, dbg);
+    return finish_launch("nrb_field_mlp_bwd");
+  }
   field_mlp_bwd_kernel<<<grid, tc::kRows, FieldBwdSmem::total, static_cast<cudaStream_t>(stream)>>>(
       to_params(p), bi, bo, samples_per_ray, M, dbg);
   return finish_launch("nrb_field_mlp_bwd");
+}
+
+// Debug: copy the phase trace of the last column-split backward launch (see NRB_TRACE) to the host.
+extern "C" int nrb_debug_bwd_trace(long long* host, int32_t n) {
+  cudaDeviceSynchronize();
+  cudaError_t e = cudaMemcpyFromSymbol(host, nrb::g_bwd_trace, sizeof(long long) * std::min(n, 2048));
+  return static_cast<int>(e);
 }

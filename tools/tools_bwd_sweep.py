@@ -1,6 +1,6 @@
 """Scratch: time nrb_hash_bwd for the main grid under the current NRB_BWD_* environment."""
 import sys, os, torch, ctypes as C
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import neuradar_b200 as nb
 from neuradar_b200 import functional as F, _lib
 from tests.parity_utils import synthetic_rays, build_hot_path, make_ray_bundle

@@ -1,6 +1,6 @@
 """Scratch: time the field MLP fwd/bwd kernels alone at config-2 size (NRB_FIELD_BWD_DEBUG bits disable stages)."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuradar_b200 import functional as Fn
 from tests.test_gpu_tensorcore import _field_inputs
 DEV = "cuda"

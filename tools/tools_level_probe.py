@@ -1,6 +1,6 @@
 """GPU probe: per-level cost of hash bwd in the production mapping (16 same-res levels)."""
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ctypes as C
 import neuradar_b200 as nb
 from neuradar_b200 import functional as F, _lib

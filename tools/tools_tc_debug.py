@@ -1,5 +1,5 @@
 import sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuradar_b200 import functional as Fn
 from tests.test_gpu_tensorcore import _field_inputs, _field_ref
 DEV = "cuda"

@@ -1,6 +1,6 @@
 """Scratch: explore tcgen05 descriptor conventions (majors, M=64 layout, LBO/SBO roles) on the GPU."""
 import itertools, sys, os, torch
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from neuradar_b200 import functional as Fn
 torch.manual_seed(0)
 dev = "cuda"
