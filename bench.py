@@ -95,7 +95,8 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, regularisers: bool = False):
+def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, regularisers: bool = False,
+                      optimizer: bool = False):
     """fwd+bwd of the reference algorithm (CPU oracle port, fp32 torch ops) on `num_rays` rays of the workload."""
     from oracle import neuradar_oracle as O
     from tests.parity_utils import scaled_pixel_area, synthetic_rays
@@ -122,6 +123,11 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, re
     pa = scaled_pixel_area(rays)
     cfg = O.PathConfig(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES)
     leaves = [main.table, *fld.geo_w, *fld.geo_b, *fld.feat_w, *fld.feat_b, fld.beta, prop.grid.table, prop.decoder_w]
+    opts = []
+    if optimizer:  # the reference's parameter groups (configs/method_configs.py:393-400)
+        opts = [torch.optim.Adam([main.table, prop.grid.table], lr=1e-2, eps=1e-15),
+                torch.optim.AdamW([t for t in leaves if t is not main.table and t is not prop.grid.table], lr=1e-2, eps=1e-15,
+                                  weight_decay=1e-7)]
 
     def step():
         for t in leaves:
@@ -132,6 +138,8 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, re
         if regularisers:
             loss = loss + O.training_losses(out)
         loss.backward()
+        for o in opts:
+            o.step()
 
     for _ in range(warmup):
         step()
@@ -147,7 +155,7 @@ def run_reference(args, rank):
         return
     sample = 4096
     steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, ms, cores = cpu_reference_run(sample, steps, warmup, regularisers=args.regularisers)
+    value, ms, cores = cpu_reference_run(sample, steps, warmup, regularisers=args.regularisers, optimizer=args.optimizer)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -183,8 +191,19 @@ def run_b200(args, rank, world, local_rank):
     n = args.rays
     model = build_hot_path(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES, seed=42, device=dev)
     model.train()
-    used = [p for name, p in model.named_parameters() if not name.startswith("proposal_fields.0")]
-    arena = GradArena(used)
+    used = [(name, p) for name, p in model.named_parameters() if not name.startswith("proposal_fields.0")]
+    opt = None
+    if args.optimizer:
+        # the reference's "hashgrids" (Adam) and "fields" (AdamW) groups, each one flat buffer and one fused kernel
+        from neuradar_b200.optim import FusedAdam, FusedAdamW
+
+        tables = [p for name, p in used if name.endswith("hash_table")]
+        others = [p for name, p in used if not name.endswith("hash_table")]
+        opts = [FusedAdam(tables, lr=1e-2, eps=1e-15), FusedAdamW(others, lr=1e-2, eps=1e-15, weight_decay=1e-7)]
+        arena_bytes = sum(g.numel() * 4 for o in opts for g in o.flat_grads())
+    else:
+        arena = GradArena([p for _, p in used])
+        arena_bytes = arena.nbytes
     rays = synthetic_rays(n, seed=42 + rank)  # each rank draws its own rays (train.py:104 seeds seed+rank)
     keys = ["origins", "directions", "pixel_area", "nears", "fars", "times", "is_lidar", "is_radar"]
     host = {k: rays[k].pin_memory() for k in keys}
@@ -197,13 +216,18 @@ def run_b200(args, rank, world, local_rank):
                             times=src["times"], metadata={"is_lidar": src["is_lidar"], "is_radar": src["is_radar"]})
 
     def step(src):
-        arena.zero()
+        if not args.optimizer:
+            arena.zero()
         out = model(bundle(src))
         loss = nb.bench_loss(out)
         if args.regularisers:
             loss = loss + nb.training_losses(out)
         loss.backward()
-        arena.all_reduce()
+        if args.optimizer:
+            for o in opts:  # sum over ranks; the average and zero_grad ride inside the fused update
+                o.step(grad_mult=o.all_reduce_grads(), zero_grad=True)
+        else:
+            arena.all_reduce()
         return loss
 
     def step_e2e():
@@ -265,6 +289,8 @@ def run_b200(args, rank, world, local_rank):
         "nrb_field_mlp_fwd": ("tensor", n_main * float(mlp_flop)),
         "nrb_field_mlp_bwd": ("tensor", n_main * float(mlp_flop) * 2),
     }
+    if args.optimizer:  # read p, g, m, v + write p, m, v, g = 32 B per parameter, averaged over the two groups' launches
+        work["nrb_adam_step"] = ("hbm", arena_bytes / 4 * 32.0 / 2)
     rooflines = {}
     for name, (bound, amount) in work.items():
         if name not in kernels:
@@ -286,9 +312,10 @@ def run_b200(args, rank, world, local_rank):
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "rays_per_gpu": n, "global_rays": total_rays,
-                   "parallelism": f"ray-sharded dp{world}, one all-reduce of a {arena.nbytes / 2**20:.0f} MiB gradient arena",
+                   "parallelism": f"ray-sharded dp{world}, one all-reduce of a {arena_bytes / 2**20:.0f} MiB gradient arena",
                    "l2": "per-step working set (saved activations + gradient arena, > 1 GB) exceeds the 126 MB L2; "
-                         "no explicit flush", "optimizer": "not part of the path (SURVEY.md 8f next-2)",
+                         "no explicit flush", "optimizer": "fused Adam (hash grids) + AdamW (MLPs) inside the step" if args.optimizer
+                   else "not part of the path (SURVEY.md 8f next-2; --optimizer adds it)",
                    "regularisers": bool(args.regularisers)},
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -300,7 +327,7 @@ def run_b200(args, rank, world, local_rank):
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, cms, cores = cpu_reference_run(4096, 2, 1, regularisers=args.regularisers)
+            v, cms, cores = cpu_reference_run(4096, 2, 1, regularisers=args.regularisers, optimizer=args.optimizer)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": "4096 of the 65536 rays per step, 2 timed fwd+bwd steps of the oracle"}
         print(json.dumps(line))
@@ -314,6 +341,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", action="store_true",
+                    help="add the fused Adam / AdamW update (SURVEY.md 8f next-2) to the step of both arms")
     ap.add_argument("--regularisers", action="store_true",
                     help="add the interlevel + distortion losses (SURVEY.md 8f next-1) to the step of both arms")
     args = ap.parse_args()

@@ -246,6 +246,28 @@ int nrb_interlevel_loss(const float* c_bins, int64_t c_stride, const float* w, i
                         int64_t cp_stride, const float* wp, int32_t Sp, float pulse_width, int64_t N,
                         float* loss_per_ray, float* grad_factor, nrb_stream_t stream);
 
+/* ---- optimiser step ----
+ * torch.optim.Adam / AdamW exactly as the reference configures them for the "hashgrids" (Adam, lr 1e-2, eps 1e-15) and
+ * "fields" (AdamW, weight_decay 1e-7) parameter groups (nerfstudio/configs/method_configs.py:393-400) and steps them
+ * through GradScaler (nerfstudio/engine/optimizers.py:159-181): one pass over a flat fp32 segment that reads p, g, m, v
+ * and writes p, m, v.  The gradient is first multiplied by grad_mult (e.g. 1 / world_size for the data-parallel
+ * average) and divided by *loss_scale when that device scalar is given (GradScaler.unscale_); when *found_inf != 0
+ * the update is skipped (GradScaler.step), zero_grad still applies; torch does not count a skipped step, so when
+ * `skipped_steps` (device float, starts at 0) is given it is incremented on a skip and the bias corrections use
+ * cfg->step - *skipped_steps: the caller keeps counting every call and never synchronises. */
+typedef struct {
+  double lr, beta1, beta2, eps, weight_decay; /* the Python floats torch.optim receives; constants such as 1 - beta2
+                                                 and lr / (1 - beta1^step) are formed in double and rounded once */
+  int32_t decoupled_weight_decay; /* 0: Adam (L2 term added to the gradient), 1: AdamW (p *= 1 - lr * wd) */
+  int32_t step;                   /* 1-based count of this update (bias corrections 1 - beta^step) */
+  float grad_mult;
+  int32_t zero_grad;              /* also write zeros to g (optimizer.zero_grad fused) */
+} nrb_adam_t;
+int nrb_adam_step(float* p, float* g, float* m, float* v, int64_t n, const nrb_adam_t* cfg, const float* loss_scale,
+                  const float* found_inf, float* skipped_steps, nrb_stream_t stream);
+/* found_inf[0] = 1.0f if any of the n gradients is inf or nan (GradScaler._unscale_grads_'s check); never cleared. */
+int nrb_grad_check(const float* g, int64_t n, float* found_inf, nrb_stream_t stream);
+
 /* ---- fused proposal round: NeuRADProposalField.get_density + RaySamples.get_weights
  * (fields/neurad_field.py:208-213, cameras/rays.py:188-210) in one kernel, one warp per ray:
  * gaussians -> contraction -> hash encode -> level weights -> Linear(L*F, 1, bias=False) -> trunc_exp -> weights.

@@ -96,6 +96,12 @@ class Spacing(C.Structure):
     _fields_ = [("lam", C.c_float), ("scaling", C.c_float)]
 
 
+class AdamCfg(C.Structure):  # nrb_adam_t
+    _fields_ = [("lr", C.c_double), ("beta1", C.c_double), ("beta2", C.c_double), ("eps", C.c_double),
+                ("weight_decay", C.c_double), ("decoupled_weight_decay", C.c_int32), ("step", C.c_int32),
+                ("grad_mult", C.c_float), ("zero_grad", C.c_int32)]
+
+
 _P = C.c_void_p
 _I32 = C.c_int32
 _I64 = C.c_int64
@@ -127,6 +133,8 @@ SIGNATURES = {
     "nrb_accumulate_fwd": [_P, _P, _I64, _I32, _I32, _P, _P],
     "nrb_accumulate_bwd": [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
     "nrb_alpha_composite_bwd": [_P, _P, C.POINTER(Intervals), _I64, _I32, _F, _I32, _P, _P, _P, _P, _P, _P, _P],
+    "nrb_adam_step": [_P, _P, _P, _P, _I64, C.POINTER(AdamCfg), _P, _P, _P, _P],
+    "nrb_grad_check": [_P, _I64, _P, _P],
     "nrb_distortion_loss": [_P, _I64, _P, _I64, _I32, _P, _P, _P],
     "nrb_interlevel_loss": [_P, _I64, _P, _I32, _P, _I64, _P, _I32, _F, _I64, _P, _P, _P],
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],

@@ -693,3 +693,25 @@ def training_losses(out: PathOutputs, interlevel_mult: float = 0.001, distortion
     proposals = [(sb, w[..., 0]) for sb, w in zip(out.sbins_list[:-1], out.weights_list[:-1])]
     inter = zipnerf_interlevel_loss(out.sbins_list[-1], w_final, proposals)
     return interlevel_mult * inter + distortion_mult * distortion_loss(out.sbins_list[-1], w_final)
+
+
+# --------------------------------------------------------------------------------------------
+# the optimiser step of the "hashgrids" / "fields" parameter groups
+# --------------------------------------------------------------------------------------------
+def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, betas: Tuple[float, float] = (0.9, 0.999),
+              eps: float = 1e-15, weight_decay: float = 0.0, decoupled: bool = False, grad_mult: float = 1.0,
+              loss_scale: float = 1.0) -> None:
+    """One in-place Adam (decoupled=False) / AdamW (True) update as torch.optim runs it for the reference
+    (configs/method_configs.py:393-400 -> engine/optimizers.py:47-52,159-181 -> torch/optim/adam.py
+    _single_tensor_adam).  `step` is the 1-based count of this update; the gradient is first multiplied by
+    grad_mult / loss_scale (data-parallel average, GradScaler.unscale_)."""
+    g = g * (grad_mult / loss_scale)
+    if decoupled:
+        p.mul_(1 - lr * weight_decay)
+    elif weight_decay != 0:
+        g = g.add(p, alpha=weight_decay)
+    m.lerp_(g, 1 - betas[0])
+    v.mul_(betas[1]).addcmul_(g, g, value=1 - betas[1])
+    bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
+    denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
+    p.addcdiv_(m, denom, value=-(lr / bc1))

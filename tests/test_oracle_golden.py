@@ -236,3 +236,24 @@ def test_losses(golden):
     for i in range(3):
         scale = float(g[f"dw{i}"].abs().max()) + 1e-30
         assert float((ws[i].grad - g[f"dw{i}"]).abs().max()) <= 1e-5 * scale, i
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 1e-3), (True, 1e-7), (True, 1e-2)])
+def test_adam_step_matches_torch_optim(decoupled, wd):
+    """the oracle's Adam / AdamW restatement against torch.optim itself (the reference uses
+    torch.optim.Adam / AdamW directly, configs/method_configs.py:393-400)."""
+    gen = torch.Generator().manual_seed(3)
+    p0 = torch.randn((257,), generator=gen) * 1e-2
+    ref_p = p0.clone().requires_grad_(True)
+    cls = torch.optim.AdamW if decoupled else torch.optim.Adam
+    opt = cls([ref_p], lr=1e-2, eps=1e-15, weight_decay=wd, foreach=False, fused=False)
+    p, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 8):
+        g = torch.randn((257,), generator=gen) * (10.0 ** float(torch.randint(-6, 1, (1,), generator=gen)))
+        ref_p.grad = g.clone()
+        opt.step()
+        O.adam_step(p, g, m, v, step, lr=1e-2, eps=1e-15, weight_decay=wd, decoupled=decoupled)
+        torch.testing.assert_close(p, ref_p.detach(), rtol=1e-6, atol=1e-9)
+    st = opt.state[ref_p]
+    torch.testing.assert_close(m, st["exp_avg"], rtol=1e-6, atol=1e-12)
+    torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
