@@ -291,6 +291,12 @@ def run_b200(args, rank, world, local_rank):
     }
     if args.optimizer:  # read p, g, m, v + write p, m, v, g = 32 B per parameter, averaged over the two groups' launches
         work["nrb_adam_step"] = ("hbm", arena_bytes / 4 * 32.0 / 2)
+    # DRAM bytes per launch from the committed ncu --set full capture (None when a kernel was not captured)
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as fh:
+            captured = json.load(fh)["kernels"] if n == RAYS_PER_GPU else {}
+    except (OSError, ValueError, KeyError):
+        captured = {}
     rooflines = {}
     for name, (bound, amount) in work.items():
         if name not in kernels:
@@ -301,7 +307,9 @@ def run_b200(args, rank, world, local_rank):
         else:
             achieved, peak, unit = amount / (mean_ms * 1e-3) / 1e12, peaks["tflops"], "TFLOP/s"
         rooflines[name] = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                           "frac": achieved / peak, "traffic": None, "peak_source": peaks["source"],
+                           "frac": achieved / peak, "traffic": captured.get(name, {}).get("dram_bytes_per_launch"),
+                           "traffic_unit": "B (ncu dram read+write per launch, profiles/r1_traffic.json)",
+                           "peak_source": peaks["source"],
                            "algorithmic_per_launch": amount, "mean_launch_ms": mean_ms,
                            "ms_per_step": mean_ms * per_step[name]["launches_per_step"]}
     # the headline entry: the kernel with the largest share of the step
