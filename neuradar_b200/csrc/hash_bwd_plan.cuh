@@ -122,6 +122,83 @@ __device__ __forceinline__ void scatter_corners(const BwdPlan& plan, int l, int 
   scatter_rows8<F>(dtable + (static_cast<size_t>(l) << log2_size) * F, c.row, gr, w);
 }
 
+// ---- the same scatter with per-corner VALUES (contributions already multiplied by their weights and summed over a run
+// of samples that share a cell, see hash_bwd_dedup_kernel)
+template <int F>
+__device__ __forceinline__ void scatter_row_v(float* __restrict__ base, uint32_t row, const float (&v)[F]) {
+  float* p = base + static_cast<size_t>(row) * F;
+  if constexpr (F == 1) {
+    atomicAdd(p, v[0]);
+  } else if constexpr (F == 2) {
+    atomicAdd(reinterpret_cast<float2*>(p), make_float2(v[0], v[1]));
+  } else {
+    atomicAdd(reinterpret_cast<float4*>(p), make_float4(v[0], v[1], v[2], v[3]));
+  }
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_x_pair_v(float* __restrict__ base, uint32_t row_f, uint32_t row_c,
+                                                 const float (&vf)[F], const float (&vc)[F]) {
+  if (row_c == row_f) {  // integral x (ceil == floor; the ceil weight is 0) or a hash collision: one reduction
+    float t[F];
+#pragma unroll
+    for (int j = 0; j < F; ++j) t[j] = vf[j] + vc[j];
+    scatter_row_v<F>(base, row_f, t);
+    return;
+  }
+  if constexpr (F <= 2) {
+    if (row_c == (row_f ^ 1u)) {
+      const bool f_low = (row_f & 1u) == 0;
+      float* p = base + static_cast<size_t>(row_f & ~1u) * F;
+      if constexpr (F == 1) {
+        atomicAdd(reinterpret_cast<float2*>(p), f_low ? make_float2(vf[0], vc[0]) : make_float2(vc[0], vf[0]));
+      } else {
+        atomicAdd(reinterpret_cast<float4*>(p), f_low ? make_float4(vf[0], vf[1], vc[0], vc[1])
+                                                      : make_float4(vc[0], vc[1], vf[0], vf[1]));
+      }
+      return;
+    }
+  }
+  scatter_row_v<F>(base, row_f, vf);
+  scatter_row_v<F>(base, row_c, vc);
+}
+
+template <int F>
+__device__ __forceinline__ void scatter_rows8_v(float* __restrict__ base, const uint32_t (&row)[8], const float (&v)[8][F]) {
+  scatter_x_pair_v<F>(base, row[3], row[0], v[3], v[0]);
+  scatter_x_pair_v<F>(base, row[2], row[1], v[2], v[1]);
+  scatter_x_pair_v<F>(base, row[7], row[4], v[7], v[4]);
+  scatter_x_pair_v<F>(base, row[6], row[5], v[6], v[5]);
+}
+
+// (xf, yf, zf) / (xc, yc, zc): integer floor / ceil coordinates of the cell (for the dense lattice replicas)
+template <int F>
+__device__ __forceinline__ void scatter_corners_v(const BwdPlan& plan, int l, int log2_size, int xf, int yf, int zf, int xc,
+                                                  int yc, int zc, const uint32_t (&hashed_rows)[8], const float (&v)[8][F],
+                                                  float* __restrict__ dtable, unsigned spread) {
+  const int copies = plan.copies[l];
+  if (copies > 1 && plan.r1[l] == 0) {
+    float* rep = plan.scratch + plan.offset[l] + static_cast<size_t>(spread % static_cast<unsigned>(copies)) * plan.stride[l];
+    scatter_rows8_v<F>(rep, hashed_rows, v);
+    return;
+  }
+  if (copies > 1) {
+    const int R1 = plan.r1[l];
+    if (xf >= 0 && yf >= 0 && zf >= 0 && xc < R1 && yc < R1 && zc < R1) {
+      float* rep = plan.scratch + plan.offset[l] + static_cast<size_t>(spread % static_cast<unsigned>(copies)) * plan.stride[l];
+      const int cx[8] = {xc, xc, xf, xf, xc, xc, xf, xf};
+      const int cy[8] = {yc, yf, yf, yc, yc, yf, yf, yc};
+      const int cz[8] = {zc, zc, zc, zc, zf, zf, zf, zf};
+      uint32_t rows[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rows[k] = static_cast<uint32_t>((cz[k] * R1 + cy[k]) * R1 + cx[k]);
+      scatter_rows8_v<F>(rep, rows, v);
+      return;
+    }
+  }
+  scatter_rows8_v<F>(dtable + (static_cast<size_t>(l) << log2_size) * F, hashed_rows, v);
+}
+
 // Adds the replicas of every replicated level into the table: one thread per lattice vertex.
 template <int F>
 __global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constant__ GridDev g,

@@ -116,6 +116,102 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ G
   scatter_corners<F>(plan, l, g.log2_size, scal, px, py, pz, c, gr, w, dtable, static_cast<unsigned>(gid >> 5));
 }
 
+// Backward scatter with run merging.  One warp = 32 consecutive samples (lane = sample), looping over the levels.
+// Samples come ray by ray, and after two importance-sampling rounds neighbours along a ray are close: on the benchmark
+// rays 67 % (finest level) to 95 % (coarsest) of adjacent samples fall into the SAME cell, i.e. update the same 8 rows.
+// The scatter kernels are bound by the number of reductions they issue (RED issue rate), so each
+// run of adjacent lanes with identical (floor, ceil) cell coordinates first adds up its 8 x F corner contributions with
+// a segmented shuffle reduction, and only the head lane of the run issues reductions.  Warps whose samples are spread
+// out (more than kDedupMaxRuns runs) skip the shuffles.  dy rows are staged through shared memory (coalesced loads,
+// XOR-swizzled 16-byte chunks) because a lane reading its own row touches 32 lines per load.
+constexpr int kDedupWarps = 8;
+constexpr int kDedupMaxRuns = 26;
+
+template <int F>
+__global__ void __launch_bounds__(kDedupWarps * 32) hash_bwd_dedup_kernel(const __grid_constant__ GridDev g,
+                                                                          const __grid_constant__ BwdPlan plan,
+                                                                          const float* __restrict__ x,
+                                                                          const float* __restrict__ std,
+                                                                          const float* __restrict__ dy,
+                                                                          float* __restrict__ dtable, int64_t M) {
+  extern __shared__ __align__(16) char dedup_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = g.num_levels, RW = L * F;  // floats per dy row (4, 8, ..., 64: checked by the launcher)
+  const int CPR = RW / 4;                  // 16-byte chunks per row
+  char* tile = dedup_smem + warp * (32 * RW * 4);
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kDedupWarps + warp) * 32;
+  if (base >= M) return;
+  const int64_t m = base + lane;
+  const bool valid = m < M;
+  const int64_t mc = valid ? m : (M - 1);
+  // coalesced copy of the 32 dy rows into the swizzled tile
+  for (int e = lane; e < 32 * CPR; e += 32) {
+    const int r = e / CPR, cc = e - r * CPR;
+    const int64_t rr = min(base + r, M - 1);
+    const float4 t = __ldg(reinterpret_cast<const float4*>(dy + rr * RW) + cc);
+    *reinterpret_cast<float4*>(tile + r * (RW * 4) + ((cc ^ (r % CPR)) << 4)) = t;
+  }
+  const float px = __ldg(x + 3 * mc), py = __ldg(x + 3 * mc + 1), pz = __ldg(x + 3 * mc + 2);
+  const float sd = std != nullptr ? __ldg(std + mc) : 0.0f;
+  __syncwarp();
+  const uint32_t mask = (1u << g.log2_size) - 1u;
+  const unsigned spread = static_cast<unsigned>(base >> 5);
+  for (int l = 0; l < L; ++l) {
+    const float scal = g.scalings[l];
+    const Cell c = locate_cell(px, py, pz, scal, mask);
+    const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
+    const int xf = static_cast<int>(floorf(sx)), yf = static_cast<int>(floorf(sy)), zf = static_cast<int>(floorf(sz));
+    const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
+    float gr[F];
+    {
+      const int f0 = l * F;  // first float of this level in the row
+      const char* rowp = tile + lane * (RW * 4);
+      if constexpr (F == 4) {
+        const float4 t = *reinterpret_cast<const float4*>(rowp + (((f0 >> 2) ^ (lane % CPR)) << 4));
+        gr[0] = t.x, gr[1] = t.y, gr[2] = t.z, gr[3] = t.w;
+      } else if constexpr (F == 2) {
+        const float2 t = *reinterpret_cast<const float2*>(rowp + (((f0 >> 2) ^ (lane % CPR)) << 4) + (f0 & 3) * 4);
+        gr[0] = t.x, gr[1] = t.y;
+      } else {
+        gr[0] = *reinterpret_cast<const float*>(rowp + (((f0 >> 2) ^ (lane % CPR)) << 4) + (f0 & 3) * 4);
+      }
+    }
+    const float lw = (std != nullptr ? level_weight(scal, sd) : 1.0f) * (valid ? 1.0f : 0.0f);
+    float w[8];
+    corner_weights(c, w);
+    float v[8][F];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+#pragma unroll
+      for (int j = 0; j < F; ++j) v[k][j] = w[k] * (gr[j] * lw);
+    // runs of adjacent lanes in the same cell
+    const int ceq = (xc == xf ? 1 : 0) | (yc == yf ? 2 : 0) | (zc == zf ? 4 : 0) | (valid ? 8 : 0);
+    const int pxf = __shfl_up_sync(kFull, xf, 1), pyf = __shfl_up_sync(kFull, yf, 1), pzf = __shfl_up_sync(kFull, zf, 1);
+    const int pce = __shfl_up_sync(kFull, ceq, 1);
+    const bool head = lane == 0 || pxf != xf || pyf != yf || pzf != zf || pce != ceq;
+    const unsigned heads = __ballot_sync(kFull, head);
+    bool issue = valid;
+    if (__popc(heads) <= kDedupMaxRuns) {
+      const unsigned above = heads & ~((2u << lane) - 1u);           // heads strictly above this lane
+      const int next_head = above != 0 ? __ffs(above) - 1 : 32;      // first lane of the next run
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const bool take = lane + d < next_head;
+        if (!__any_sync(kFull, take)) break;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+#pragma unroll
+          for (int j = 0; j < F; ++j) {
+            const float t = __shfl_down_sync(kFull, v[k][j], d);
+            v[k][j] += take ? t : 0.0f;
+          }
+      }
+      issue = valid && head;
+    }
+    if (issue) scatter_corners_v<F>(plan, l, g.log2_size, xf, yf, zf, xc, yc, zc, c.row, v, dtable, spread);
+  }
+}
+
 __global__ void __launch_bounds__(256) frustum_gaussians_kernel(const float* __restrict__ origins,
                                                                 const float* __restrict__ directions,
                                                                 const float* __restrict__ pixel_area,
@@ -186,6 +282,16 @@ static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float
   if (int rc = prepare_bwd_plan(grid, M, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
   const int64_t total = M * grid->num_levels;
   const unsigned blocks = blocks_for(total, 256);
+  static const bool dedup = env_or("NRB_HASH_BWD_DEDUP", 1.0) != 0.0;
+  const int row_floats = grid->num_levels * F;
+  if (dedup && dx == nullptr && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
+    const size_t smem = static_cast<size_t>(kDedupWarps) * 32 * row_floats * 4;
+    cudaError_t e = cudaFuncSetAttribute(hash_bwd_dedup_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    hash_bwd_dedup_kernel<F><<<blocks_for(M, kDedupWarps * 32), kDedupWarps * 32, smem, s>>>(g, plan, x, std, dy, dtable, M);
+    launch_fold<F>(grid, plan, dtable, vertices, s);
+    return finish_launch("nrb_hash_bwd");
+  }
   if (dx != nullptr) {
     hash_bwd_kernel<F, true><<<blocks, 256, 0, s>>>(g, plan, x, std, dy, dtable, dx, total);
   } else {
