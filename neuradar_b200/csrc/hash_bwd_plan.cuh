@@ -199,6 +199,46 @@ __device__ __forceinline__ void scatter_corners_v(const BwdPlan& plan, int l, in
   scatter_rows8_v<F>(dtable + (static_cast<size_t>(l) << log2_size) * F, hashed_rows, v);
 }
 
+// Run merging (called by all 32 lanes of a converged warp whose lanes hold CONSECUTIVE samples of a ray): lanes whose
+// points fall into the same cell of level l (identical floor / ceil coordinates) update the same 8 rows, so each run of
+// adjacent such lanes adds up its 8 x F corner contributions v (already weighted) with a segmented shuffle reduction
+// and only the head lane of the run issues reductions.  Warps whose samples are spread out (more than kMergeMaxRuns
+// runs) skip the shuffles.  The scatter kernels are bound by the NUMBER of reductions they issue.
+constexpr int kMergeMaxRuns = 26;
+
+template <int F>
+__device__ __forceinline__ void merge_runs_and_scatter(const BwdPlan& plan, int l, int log2_size, float px, float py,
+                                                       float pz, float scal, const Cell& c, float (&v)[8][F], bool valid,
+                                                       int lane, float* __restrict__ dtable, unsigned spread) {
+  const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
+  const int xf = static_cast<int>(floorf(sx)), yf = static_cast<int>(floorf(sy)), zf = static_cast<int>(floorf(sz));
+  const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
+  const int ceq = (xc == xf ? 1 : 0) | (yc == yf ? 2 : 0) | (zc == zf ? 4 : 0) | (valid ? 8 : 0);
+  const int pxf = __shfl_up_sync(kFull, xf, 1), pyf = __shfl_up_sync(kFull, yf, 1), pzf = __shfl_up_sync(kFull, zf, 1);
+  const int pce = __shfl_up_sync(kFull, ceq, 1);
+  const bool head = lane == 0 || pxf != xf || pyf != yf || pzf != zf || pce != ceq;
+  const unsigned heads = __ballot_sync(kFull, head);
+  bool issue = valid;
+  if (__popc(heads) <= kMergeMaxRuns) {
+    const unsigned above = heads & ~((2u << lane) - 1u);       // heads strictly above this lane
+    const int next_head = above != 0 ? __ffs(above) - 1 : 32;  // first lane of the next run
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const bool take = lane + d < next_head;
+      if (!__any_sync(kFull, take)) break;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+#pragma unroll
+        for (int j = 0; j < F; ++j) {
+          const float t = __shfl_down_sync(kFull, v[k][j], d);
+          v[k][j] += take ? t : 0.0f;
+        }
+    }
+    issue = valid && head;
+  }
+  if (issue) scatter_corners_v<F>(plan, l, log2_size, xf, yf, zf, xc, yc, zc, c.row, v, dtable, spread);
+}
+
 // Adds the replicas of every replicated level into the table: one thread per lattice vertex.
 template <int F>
 __global__ void __launch_bounds__(256) hash_bwd_fold_kernel(const __grid_constant__ GridDev g,

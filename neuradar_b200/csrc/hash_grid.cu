@@ -121,11 +121,10 @@ __global__ void __launch_bounds__(256) hash_bwd_kernel(const __grid_constant__ G
 // rays 67 % (finest level) to 95 % (coarsest) of adjacent samples fall into the SAME cell, i.e. update the same 8 rows.
 // The scatter kernels are bound by the number of reductions they issue (RED issue rate), so each
 // run of adjacent lanes with identical (floor, ceil) cell coordinates first adds up its 8 x F corner contributions with
-// a segmented shuffle reduction, and only the head lane of the run issues reductions.  Warps whose samples are spread
-// out (more than kDedupMaxRuns runs) skip the shuffles.  dy rows are staged through shared memory (coalesced loads,
-// XOR-swizzled 16-byte chunks) because a lane reading its own row touches 32 lines per load.
+// a segmented shuffle reduction, and only the head lane of the run issues reductions (merge_runs_and_scatter,
+// hash_bwd_plan.cuh).  dy rows are staged through shared memory (coalesced loads, XOR-swizzled 16-byte chunks) because
+// a lane reading its own row touches 32 lines per load.
 constexpr int kDedupWarps = 8;
-constexpr int kDedupMaxRuns = 26;
 
 template <int F>
 __global__ void __launch_bounds__(kDedupWarps * 32) hash_bwd_dedup_kernel(const __grid_constant__ GridDev g,
@@ -159,9 +158,6 @@ __global__ void __launch_bounds__(kDedupWarps * 32) hash_bwd_dedup_kernel(const 
   for (int l = 0; l < L; ++l) {
     const float scal = g.scalings[l];
     const Cell c = locate_cell(px, py, pz, scal, mask);
-    const float sx = mul(px, scal), sy = mul(py, scal), sz = mul(pz, scal);
-    const int xf = static_cast<int>(floorf(sx)), yf = static_cast<int>(floorf(sy)), zf = static_cast<int>(floorf(sz));
-    const int xc = static_cast<int>(ceilf(sx)), yc = static_cast<int>(ceilf(sy)), zc = static_cast<int>(ceilf(sz));
     float gr[F];
     {
       const int f0 = l * F;  // first float of this level in the row
@@ -184,31 +180,7 @@ __global__ void __launch_bounds__(kDedupWarps * 32) hash_bwd_dedup_kernel(const 
     for (int k = 0; k < 8; ++k)
 #pragma unroll
       for (int j = 0; j < F; ++j) v[k][j] = w[k] * (gr[j] * lw);
-    // runs of adjacent lanes in the same cell
-    const int ceq = (xc == xf ? 1 : 0) | (yc == yf ? 2 : 0) | (zc == zf ? 4 : 0) | (valid ? 8 : 0);
-    const int pxf = __shfl_up_sync(kFull, xf, 1), pyf = __shfl_up_sync(kFull, yf, 1), pzf = __shfl_up_sync(kFull, zf, 1);
-    const int pce = __shfl_up_sync(kFull, ceq, 1);
-    const bool head = lane == 0 || pxf != xf || pyf != yf || pzf != zf || pce != ceq;
-    const unsigned heads = __ballot_sync(kFull, head);
-    bool issue = valid;
-    if (__popc(heads) <= kDedupMaxRuns) {
-      const unsigned above = heads & ~((2u << lane) - 1u);           // heads strictly above this lane
-      const int next_head = above != 0 ? __ffs(above) - 1 : 32;      // first lane of the next run
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const bool take = lane + d < next_head;
-        if (!__any_sync(kFull, take)) break;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-#pragma unroll
-          for (int j = 0; j < F; ++j) {
-            const float t = __shfl_down_sync(kFull, v[k][j], d);
-            v[k][j] += take ? t : 0.0f;
-          }
-      }
-      issue = valid && head;
-    }
-    if (issue) scatter_corners_v<F>(plan, l, g.log2_size, xf, yf, zf, xc, yc, zc, c.row, v, dtable, spread);
+    merge_runs_and_scatter<F>(plan, l, g.log2_size, px, py, pz, scal, c, v, valid, lane, dtable, spread);
   }
 }
 

@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     const __grid_constant__ PropGrid g, const __grid_constant__ BwdPlan plan, const float* __restrict__ origins, const float* __restrict__ directions,
     const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
     const float* __restrict__ saved_feats, const float* __restrict__ saved_pre, const float* __restrict__ dweights,
-    const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder) {
+    const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder, int merge) {
   __shared__ float s_ddec[NRB_MAX_LEVELS * 4];
   __shared__ float s_dec[NRB_MAX_LEVELS * 4];
   const int lane = threadIdx.x & 31;
@@ -148,30 +148,39 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     float ddec[NRB_MAX_LEVELS * F];
 #pragma unroll
     for (int q = 0; q < NRB_MAX_LEVELS * F; ++q) ddec[q] = 0.0f;
+    const unsigned spread = static_cast<unsigned>(blockIdx.x * kPropWarps + (threadIdx.x >> 5));
 #pragma unroll
     for (int c = 0; c < kMaxChunks; ++c) {
-      if (c * 32 < S) {
+      if (c * 32 < S) {  // warp-uniform: all lanes take part in the run merging below
         const int i = c * 32 + lane;
-        if (i < S) {
-          const float gpre = gdens[c] * expf(fminf(fmaxf(pre[c], -15.0f), 15.0f));
-          const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, st[i], en[i], scale);
-          const float* sf = saved_feats + (n * S + i) * LF;
+        const bool act = i < S;
+        const int ic = act ? i : (S - 1);
+        const float gpre = act ? gdens[c] * expf(fminf(fmaxf(pre[c], -15.0f), 15.0f)) : 0.0f;
+        const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, st[ic], en[ic], scale);
+        const float* sf = saved_feats + (n * S + ic) * LF;
 #pragma unroll
-          for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
-            if (l < g.num_levels) {
-              const float scal = g.scalings[l];
-              const Cell cell = locate_cell(q.x, q.y, q.z, scal, mask);
-              const float lw = level_weight(scal, q.std);
-              float gr[F];
+        for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
+          if (l < g.num_levels) {
+            const float scal = g.scalings[l];
+            const Cell cell = locate_cell(q.x, q.y, q.z, scal, mask);
+            const float lw = level_weight(scal, q.std);
+            float gr[F];
 #pragma unroll
-              for (int j = 0; j < F; ++j) {
-                ddec[l * F + j] = fmaf(gpre, sf[l * F + j], ddec[l * F + j]);
-                gr[j] = gpre * s_dec[l * F + j] * lw;
-              }
-              float w8[8];
-              corner_weights(cell, w8);
-              scatter_corners<F>(plan, l, g.log2_size, scal, q.x, q.y, q.z, cell, gr, w8, dtable,
-                                 static_cast<unsigned>(blockIdx.x * kPropWarps + (threadIdx.x >> 5)));
+            for (int j = 0; j < F; ++j) {
+              ddec[l * F + j] = fmaf(gpre, sf[l * F + j], ddec[l * F + j]);
+              gr[j] = gpre * s_dec[l * F + j] * lw;
+            }
+            float w8[8];
+            corner_weights(cell, w8);
+            if (merge) {
+              float v[8][F];
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
+              merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act, lane, dtable, spread);
+            } else if (act) {
+              scatter_corners<F>(plan, l, g.log2_size, scal, q.x, q.y, q.z, cell, gr, w8, dtable, spread);
             }
           }
         }
@@ -255,10 +264,12 @@ extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
   BwdPlan plan;
   int64_t vertices = 0;
   if (int rc = prepare_bwd_plan(grid, N * iv->num_samples, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
+  // merge runs of adjacent samples of a ray that share a cell before scattering (hash_bwd_plan.cuh)
+  static const int merge = env_or("NRB_PROP_BWD_MERGE", 1.0) != 0.0 ? 1 : 0;
 #define NRB_LAUNCH(F)                                                                                              \
   proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, plan, rays->origins, rays->directions, rays->pixel_area,  \
                                                             static_scale, *iv, N, saved_feats, saved_pre,          \
-                                                            dweights, ddensity, dtable, ddecoder_w)
+                                                            dweights, ddensity, dtable, ddecoder_w, merge)
   switch (grid->features_per_level) {
     case 1: NRB_LAUNCH(1); break;
     case 2: NRB_LAUNCH(2); break;
