@@ -45,6 +45,58 @@ __global__ void __launch_bounds__(256) hash_fwd_kernel(const __grid_constant__ G
   reinterpret_cast<V*>(out)[gid] = o;
 }
 
+// Sample-major forward: one warp = 32 consecutive samples (lane = sample), looping over the levels.  Consecutive
+// samples of a ray mostly fall into the same cell (see hash_bwd_dedup_kernel), so the 32 gathers of one corner hit a
+// handful of distinct rows and coalesce in L1/TEX, which is the unit that bounds the level-major kernel above (ncu:
+// 95 % busy, one line per lane).  The 32 output rows are assembled in a swizzled shared-memory tile and written with
+// coalesced 16-byte stores.
+constexpr int kFwdWarps = 8;
+
+template <int F>
+__global__ void __launch_bounds__(kFwdWarps * 32) hash_fwd_rows_kernel(const __grid_constant__ GridDev g,
+                                                                      const float* __restrict__ x,
+                                                                      const float* __restrict__ std,
+                                                                      float* __restrict__ out, int64_t M) {
+  extern __shared__ __align__(16) char fwd_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = g.num_levels, RW = L * F, CPR = RW / 4;
+  char* tile = fwd_smem + warp * (32 * RW * 4);
+  const int64_t base = (static_cast<int64_t>(blockIdx.x) * kFwdWarps + warp) * 32;
+  if (base >= M) return;
+  const int64_t mc = min(base + lane, M - 1);
+  const float px = __ldg(x + 3 * mc), py = __ldg(x + 3 * mc + 1), pz = __ldg(x + 3 * mc + 2);
+  const float sd = std != nullptr ? __ldg(std + mc) : 0.0f;
+  const uint32_t mask = (1u << g.log2_size) - 1u;
+  char* rowp = tile + lane * (RW * 4);
+  for (int l = 0; l < L; ++l) {
+    const float scal = g.scalings[l];
+    const Cell c = locate_cell(px, py, pz, scal, mask);
+    float v[F];
+    interpolate<F>(g.table + (static_cast<size_t>(l) << g.log2_size) * F, c, v);
+    if (std != nullptr) {
+      const float w = level_weight(scal, sd);
+#pragma unroll
+      for (int j = 0; j < F; ++j) v[j] *= w;
+    }
+    const int f0 = l * F;
+    char* dst = rowp + (((f0 >> 2) ^ (lane % CPR)) << 4) + (f0 & 3) * 4;
+    if constexpr (F == 4) {
+      *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+    } else if constexpr (F == 2) {
+      *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+    } else {
+      *reinterpret_cast<float*>(dst) = v[0];
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < 32 * CPR; e += 32) {
+    const int r = e / CPR, cc = e - r * CPR;
+    if (base + r < M)
+      reinterpret_cast<float4*>(out + (base + r) * RW)[cc] =
+          *reinterpret_cast<const float4*>(tile + r * (RW * 4) + ((cc ^ (r % CPR)) << 4));
+  }
+}
+
 __global__ void __launch_bounds__(256) hash_indices_kernel(const __grid_constant__ GridDev g, const float* __restrict__ x,
                                                            int64_t* __restrict__ idx, int64_t total) {
   const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -218,6 +270,25 @@ extern "C" int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float*
   const GridDev g = to_dev(grid);
   auto s = static_cast<cudaStream_t>(stream);
   const unsigned blocks = blocks_for(total, 256);
+  static const bool rows = env_or("NRB_HASH_FWD_ROWS", 1.0) != 0.0;
+  const int row_floats = grid->num_levels * grid->features_per_level;
+  if (rows && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
+    const size_t smem = static_cast<size_t>(kFwdWarps) * 32 * row_floats * 4;
+    const unsigned nb = blocks_for(M, kFwdWarps * 32);
+#define NRB_ROWS(F)                                                                                                    \
+  {                                                                                                                    \
+    cudaError_t e = cudaFuncSetAttribute(hash_fwd_rows_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
+    hash_fwd_rows_kernel<F><<<nb, kFwdWarps * 32, smem, s>>>(g, x, std, out, M);                                        \
+  }
+    switch (grid->features_per_level) {
+      case 1: NRB_ROWS(1) break;
+      case 2: NRB_ROWS(2) break;
+      default: NRB_ROWS(4) break;
+    }
+#undef NRB_ROWS
+    return finish_launch("nrb_hash_fwd");
+  }
   switch (grid->features_per_level) {
     case 1: hash_fwd_kernel<1><<<blocks, 256, 0, s>>>(g, x, std, out, total); break;
     case 2: hash_fwd_kernel<2><<<blocks, 256, 0, s>>>(g, x, std, out, total); break;
