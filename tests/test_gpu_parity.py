@@ -58,6 +58,38 @@ def test_hash_indices_bit_exact(nb, golden):
     assert torch.equal(Fn.hash_indices(xo.to(DEV), spec).cpu(), want)
 
 
+@pytest.mark.parametrize("L,F,M", [(16, 2, 1000), (16, 2, 33), (16, 2, 31), (8, 4, 4097), (4, 4, 640), (6, 1, 500)])
+def test_hash_clustered_samples_run_merging(nb, L, F, M):
+    """The sample-major forward and the run-merging backward on what they are built for: ray-ordered samples that
+    pile into the same cells (identical points, integral coordinates, runs crossing warp boundaries), ragged M, and
+    the shapes that take the level-major fallback (M < 32, L*F not a power of two).  The table gradient must equal
+    the oracle's index_add whatever the grouping."""
+    from neuradar_b200 import functional as Fn
+
+    g = torch.Generator().manual_seed(M + L)
+    log2T = 12
+    anchors = torch.rand((max(M // 40, 1), 3), generator=g)
+    x = anchors.repeat_interleave(40, dim=0)[:M].clone()
+    if x.shape[0] < M:
+        x = torch.cat([x, torch.rand((M - x.shape[0], 3), generator=g)])
+    x = x + torch.rand((M, 3), generator=g) * torch.rand((M, 1), generator=g).pow(4) * 0.02  # mostly tiny offsets
+    x[5:9] = x[4]                          # exactly identical points
+    x[10:14] = torch.tensor([0.5, 0.25, 0.75])  # integral grid coordinates on the power-of-two levels
+    x = x.clamp(0, 1)
+    scal = O.level_scalings(L, 16, 512)
+    spec = spec_for(nb, L, F, log2T, 16, 512)
+    table = (torch.rand(((1 << log2T) * L, F), generator=g) * 2 - 1)
+    dy = torch.randn((M, L * F), generator=g)
+    t_ref = table.clone().requires_grad_(True)
+    y_ref = O.hash_encode(x, t_ref, scal, log2T)
+    (y_ref * dy).sum().backward()
+    t_dev = table.to(DEV).requires_grad_(True)
+    y = Fn.hash_encode(x.to(DEV), t_dev, spec)
+    assert rel_err(y, y_ref) <= 1e-6
+    (y * dy.to(DEV)).sum().backward()
+    assert rel_err(t_dev.grad, t_ref.grad) <= 1e-5  # fp32 sums in a different order
+
+
 @pytest.mark.parametrize("F", [1, 2, 4])
 def test_hash_forward_backward_golden(nb, golden, F):
     from neuradar_b200 import functional as Fn
