@@ -199,10 +199,11 @@ def run_b200(args, rank, world, local_rank):
 
         tables = [p for name, p in used if name.endswith("hash_table")]
         others = [p for name, p in used if not name.endswith("hash_table")]
-        opts = [FusedAdam(tables, lr=1e-2, eps=1e-15), FusedAdamW(others, lr=1e-2, eps=1e-15, weight_decay=1e-7)]
+        opts = [FusedAdam(tables, lr=1e-2, eps=1e-15, direct_scatter=True),
+                FusedAdamW(others, lr=1e-2, eps=1e-15, weight_decay=1e-7)]
         arena_bytes = sum(g.numel() * 4 for o in opts for g in o.flat_grads())
     else:
-        arena = GradArena([p for _, p in used])
+        arena = GradArena([p for _, p in used], direct_scatter=True)
         arena_bytes = arena.nbytes
     rays = synthetic_rays(n, seed=42 + rank)  # each rank draws its own rays (train.py:104 seeds seed+rank)
     keys = ["origins", "directions", "pixel_area", "nears", "fars", "times", "is_lidar", "is_radar"]

@@ -32,9 +32,12 @@ class GradArena:
 
     `param.grad` is pointed into the arena, so autograd accumulates straight into it, `zero()` is one memset and
     `all_reduce()` is one collective.  Parameters that receive no gradient in a step (e.g. the never-evaluated
-    first proposal field) simply contribute zeros, which is what DDP's find_unused_parameters does."""
+    first proposal field) simply contribute zeros, which is what DDP's find_unused_parameters does.
+    `direct_scatter=True` additionally lets the hash-grid backward kernels add straight into the arena
+    (functional.grad_sink_of) instead of returning a table-sized temporary to autograd."""
 
-    def __init__(self, params: Iterable[nn.Parameter], skip_unused: Optional[List[nn.Parameter]] = None):
+    def __init__(self, params: Iterable[nn.Parameter], skip_unused: Optional[List[nn.Parameter]] = None,
+                 direct_scatter: bool = False):
         skip = {id(p) for p in (skip_unused or [])}
         self.params = [p for p in params if p.requires_grad and id(p) not in skip]
         if not self.params:
@@ -49,6 +52,8 @@ class GradArena:
         self.flat = torch.zeros((total,), device=dev, dtype=torch.float32)
         for p, off in zip(self.params, offsets):
             p.grad = self.flat[off : off + p.numel()].view_as(p)
+            if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
+                p._nrb_grad_sink = p.grad  # hash tables: the scatter kernels add straight into the arena
 
     @property
     def nbytes(self) -> int:

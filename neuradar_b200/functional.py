@@ -164,10 +164,22 @@ def side_stream(device, index: int = 0) -> "torch.cuda.Stream":
 # ------------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------------
+def grad_sink_of(table: Tensor) -> Optional[Tensor]:
+    """Opt-in direct gradient accumulation: when the owner of the flat gradient buffer (dist.GradArena, optim.FusedAdam)
+    marked a hash table with `_nrb_grad_sink` (a view with the table's shape), the scatter kernels add straight into
+    it and the autograd Function returns no gradient for the table.  This skips a zero-fill of a table-sized temporary
+    and AccumulateGrad's read-add-write of it (3 x 64 MiB of traffic for the main grid) per backward."""
+    sink = getattr(table, "_nrb_grad_sink", None)
+    if sink is None or sink.shape != table.shape or sink.dtype != torch.float32 or not sink.is_contiguous():
+        return None
+    return sink
+
+
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, table, std, spec: GridSpec, samples_per_ray: int = 0):
+        ctx.sink = grad_sink_of(table)
         x = f32c(x)
         table = f32c(table)
         std = None if std is None else f32c(std.reshape(-1))
@@ -187,13 +199,13 @@ class _HashEncode(torch.autograd.Function):
         spec = ctx.spec
         dy = f32c(dy)
         need_dx = ctx.needs_input_grad[0]
-        dtable = torch.zeros_like(table)
+        dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
         dx = torch.empty_like(x) if need_dx else None
         g = spec.struct(table)
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), x.shape[0])), x.device)
         _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], ws, ws_bytes,
                   stream_ptr(), tag="nrb_hash_bwd:" + spec.tag)
-        return dx, dtable, None, None, None
+        return dx, (None if ctx.sink is not None else dtable), None, None, None
 
 
 def hash_encode(x: Tensor, table: Tensor, spec: GridSpec, std: Optional[Tensor] = None, samples_per_ray: int = 0) -> Tensor:
@@ -634,6 +646,7 @@ class _ProposalRound(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, table, decoder_w, rays: RayData, iv: SampleIntervals, spec: GridSpec, scale: float):
+        ctx.sink = grad_sink_of(table)
         table = f32c(table)
         dec = f32c(decoder_w.reshape(-1))
         N, S = rays.num_rays, iv.num_samples
@@ -655,7 +668,7 @@ class _ProposalRound(torch.autograd.Function):
     @custom_bwd(device_type="cuda")
     def backward(ctx, ddensity, dweights):
         table, dec, feats, pre = ctx.saved_tensors
-        dtable = torch.zeros_like(table)
+        dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
         ddec = torch.zeros_like(dec)
         ddensity = None if ddensity is None else f32c(ddensity)
         dweights = None if dweights is None else f32c(dweights)
@@ -664,7 +677,7 @@ class _ProposalRound(torch.autograd.Function):
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), n_pts)), table.device)
         _lib.call("nrb_proposal_bwd", C.byref(r), C.byref(g), ptr(dec), ctx.scale, C.byref(i), ptr(feats), ptr(pre),
                   ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, stream_ptr())
-        return dtable, ddec.reshape(ctx.dec_shape), None, None, None, None
+        return (None if ctx.sink is not None else dtable), ddec.reshape(ctx.dec_shape), None, None, None, None
 
 
 def proposal_round(

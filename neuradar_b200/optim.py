@@ -25,7 +25,7 @@ import ctypes as C
 class _FlatGroup:
     """Parameters of one group re-homed into one flat buffer; .grad of each is a view of the flat gradient."""
 
-    def __init__(self, params: List[torch.nn.Parameter]):
+    def __init__(self, params: List[torch.nn.Parameter], direct_scatter: bool = False):
         dev = params[0].device
         offsets, total = [], 0
         for p in params:
@@ -47,6 +47,8 @@ class _FlatGroup:
             if p.grad is not None:
                 gview.copy_(p.grad)
             p.grad = gview
+            if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
+                p._nrb_grad_sink = gview  # hash tables: the scatter kernels add straight into the flat gradient
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -55,14 +57,15 @@ class FusedAdam(torch.optim.Optimizer):
     _decoupled = False
     _step_supports_amp_scaling = True  # GradScaler hands us grad_scale / found_inf instead of unscaling itself
 
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0):
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 direct_scatter: bool = False):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._flat: List[_FlatGroup] = []
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.requires_grad]
-            self._flat.append(_FlatGroup(ps))
+            self._flat.append(_FlatGroup(ps, direct_scatter))
             group["step"] = 0
         # GradScaler.step sets (and deletes) self.grad_scale / self.found_inf around step(); they must not pre-exist
 
@@ -109,6 +112,8 @@ class FusedAdam(torch.optim.Optimizer):
                     else:
                         gview.zero_()
                     p.grad = gview
+                    if getattr(p, "_nrb_grad_sink", None) is not None:
+                        p._nrb_grad_sink = gview
             group["step"] += 1
             cfg = AdamCfg(float(group["lr"]), float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                           float(group["weight_decay"]), int(self._decoupled), int(group["step"]), float(grad_mult),
@@ -156,5 +161,6 @@ class FusedAdamW(FusedAdam):
 
     _decoupled = True
 
-    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2):
-        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+    def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
+                 direct_scatter: bool = False):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, direct_scatter=direct_scatter)

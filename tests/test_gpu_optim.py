@@ -121,3 +121,33 @@ def test_adam_full_size_streaming_properties():
     p.grad.copy_(sign * 3.0)
     opt.step()  # first step: m / (1 - beta1) = g, sqrt(v / (1 - beta2)) = |g|
     assert rel_err(p, -1e-2 * sign) < 1e-6
+
+
+def test_direct_scatter_into_arena_matches_autograd_accumulation():
+    """GradArena(direct_scatter=True): the hash-grid backward kernels add straight into the arena views; gradients
+    must equal the ordinary autograd accumulation (also when a table is used twice, as the late-binding proposal
+    field is) and accumulate over two backward passes."""
+    import neuradar_b200 as nb
+    from neuradar_b200.dist import GradArena
+    from tests.parity_utils import FixedJitter, build_hot_path, make_ray_bundle, synthetic_rays
+
+    n = 512
+    rays = synthetic_rays(n, seed=9)
+    gen = torch.Generator().manual_seed(10)
+    jit = [torch.rand((n, 65), generator=gen), torch.rand((n, 1), generator=gen), torch.rand((n, 1), generator=gen)]
+    grads = []
+    for direct in (False, True):
+        model = build_hot_path(log2_main=14, log2_prop=14, num_proposal_samples=(64, 48), num_nerf_samples=48,
+                               late_binding=True, table_gain=(300.0, 2000.0), seed=4, device=DEV)
+        model.train()
+        used = [p for name, p in model.named_parameters() if not name.startswith("proposal_fields.0")]
+        arena = GradArena(used, direct_scatter=direct)
+        assert any(getattr(p, "_nrb_grad_sink", None) is not None for p in used) == direct
+        for _ in range(2):  # gradients accumulate across backward passes, like .grad does
+            with FixedJitter(jit):
+                out = model(make_ray_bundle(rays, DEV))
+            nb.bench_loss(out).backward()
+        grads.append(arena.flat.clone())
+    scale = float(grads[0].abs().max())
+    assert scale > 0
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * scale  # atomics: last-bit differences only
