@@ -231,7 +231,7 @@ __device__ __forceinline__ void merge_runs_and_scatter(const BwdPlan& plan, int 
 #pragma unroll
         for (int j = 0; j < F; ++j) {
           const float t = __shfl_down_sync(kFull, v[k][j], d);
-          v[k][j] += take ? t : 0.0f;
+          if (take) v[k][j] += t;  // one predicated FADD
         }
     }
     issue = valid && head;
