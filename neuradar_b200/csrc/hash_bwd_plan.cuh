@@ -288,10 +288,12 @@ inline double env_or(const char* name, double dflt) {
 }
 
 inline int64_t plan_hash_bwd(const nrb_grid_t* grid, int64_t M, BwdPlan* plan) {
-  // tunables (defaults chosen on B200 with tools/sweep): replicas ~ scale * table_rows / vertices,
-  // at most cap_mb per level; levels that already fill the table get `hashed` replicas of the hashed table itself
-  static const double scale = env_or("NRB_BWD_SCALE", 4.0), cap_mb = env_or("NRB_BWD_CAP_MB", 32.0);
-  static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 4.0));
+  // Tunables, swept on B200 at config 2 (tools/sweep_bwd_env*.sh).  Dense-lattice replicas for the
+  // coarse levels: copies ~ scale * table_rows / vertices, at most cap_mb per level.  Replicas of the HASHED level
+  // tables (hashed > 1) paid off before run merging (3.2 -> 2.4 ms); with it they only cost L2 capacity, so they are off
+  // by default and remain available for sample orders that do not merge (NRB_BWD_HASHED_COPIES / _LEVELS).
+  static const double scale = env_or("NRB_BWD_SCALE", 1.0), cap_mb = env_or("NRB_BWD_CAP_MB", 32.0);
+  static const int hashed = static_cast<int>(env_or("NRB_BWD_HASHED_COPIES", 1.0));
   static const int hashed_levels = static_cast<int>(env_or("NRB_BWD_HASHED_LEVELS", 4.0));
   const int F = grid->features_per_level;
   const int64_t T = int64_t{1} << grid->log2_hashmap_size;

@@ -60,17 +60,19 @@ __global__ void __launch_bounds__(256) adam_step_kernel(float* __restrict__ p, f
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
     if (!skip) {
+      // moments and gradients stream through (evict-first); the parameters are written with the default policy so that
+      // the tables are still L2 resident when the next forward gathers from them
       float4 pp = reinterpret_cast<float4*>(p)[i], gg = __ldcs(reinterpret_cast<const float4*>(g) + i);
-      float4 mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+      float4 mm = __ldcs(reinterpret_cast<const float4*>(m) + i), vv = __ldcs(reinterpret_cast<const float4*>(v) + i);
       adam_update(pp.x, gg.x, mm.x, vv.x, c, gmul, step_size, bc2_sqrt);
       adam_update(pp.y, gg.y, mm.y, vv.y, c, gmul, step_size, bc2_sqrt);
       adam_update(pp.z, gg.z, mm.z, vv.z, c, gmul, step_size, bc2_sqrt);
       adam_update(pp.w, gg.w, mm.w, vv.w, c, gmul, step_size, bc2_sqrt);
       reinterpret_cast<float4*>(p)[i] = pp;
-      reinterpret_cast<float4*>(m)[i] = mm;
-      reinterpret_cast<float4*>(v)[i] = vv;
+      __stcs(reinterpret_cast<float4*>(m) + i, mm);
+      __stcs(reinterpret_cast<float4*>(v) + i, vv);
     }
-    if (c.zero_grad) reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c.zero_grad) __stcs(reinterpret_cast<float4*>(g) + i, make_float4(0.f, 0.f, 0.f, 0.f));
   }
   // tail (n % 4 elements)
   const int64_t tail0 = n4 << 2;
