@@ -594,21 +594,23 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
 }
 
 // 3xTF32 chain with A (hi / lo) in TMEM columns and B (hi / lo) K-major canonical tiles of b_cols columns.  One thread.
-// Back-to-back tcgen05.mma into the SAME accumulator serialise on its read-modify-write (measured ~55 cycles per
-// instruction for these small shapes, whatever the operand source), so every K step gets its own accumulator
-// (d_tmem + k * d_stride columns, chains of three) and the consumer adds the k_red / 8 partial results.
-__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, int d_stride, int n, uint32_t a_hi_tmem, uint32_t a_lo_tmem,
-                                              uint32_t b_hi, uint32_t b_lo, int b_cols, int k_red) {
+// (Measured: these small instructions cost ~35-55 cycles each whatever the operand source and whether or not
+//  consecutive ones share an accumulator - one accumulator per K step bought nothing and cost four TMEM loads.)
+__device__ __forceinline__ void issue_gemm_ts(uint32_t d_tmem, int n, uint32_t a_hi_tmem, uint32_t a_lo_tmem, uint32_t b_hi,
+                                              uint32_t b_lo, int b_cols, int k_red) {
   const uint32_t idesc = make_idesc_m(128, n, 0, 0);
   const uint32_t b_sbo = static_cast<uint32_t>(b_cols / 4) * 128u;
-  const uint64_t bh = make_desc(b_hi, 128, b_sbo), bl = make_desc(b_lo, 128, b_sbo);
-  const int steps = k_red / 8;
+  uint64_t bh = make_desc(b_hi, 128, b_sbo), bl = make_desc(b_lo, 128, b_sbo);
+  bool acc = false;
 #pragma unroll 4
-  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_lo_tmem + 8 * k, bh + 16 * k, idesc, false);
-#pragma unroll 4
-  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_hi_tmem + 8 * k, bl + 16 * k, idesc, true);
-#pragma unroll 4
-  for (int k = 0; k < steps; ++k) mma_tf32_ts(d_tmem + k * d_stride, a_hi_tmem + 8 * k, bh + 16 * k, idesc, true);
+  for (int k = 0; k < k_red / 8; ++k) {
+    mma_tf32_ts(d_tmem, a_lo_tmem + 8 * k, bh, idesc, acc);  // small terms first
+    mma_tf32_ts(d_tmem, a_hi_tmem + 8 * k, bl, idesc, true);
+    mma_tf32_ts(d_tmem, a_hi_tmem + 8 * k, bh, idesc, true);
+    acc = true;
+    bh += 16;
+    bl += 16;
+  }
 }
 
 }  // namespace tc

@@ -36,7 +36,8 @@ struct FieldSaved {  // activations kept for the backward pass, feature-major wi
   int64_t ld;        // multiple of 128, >= M
 };
 
-constexpr int kTmemCols = 64;
+constexpr int kTmemCols = 256;               // accumulator (48) + the A operand as tf32 hi / lo (2 x 48); 2 CTAs per SM
+constexpr int kFwdAHi = 64, kFwdALo = 128;  // TMEM columns of the A operand
 // layer geometry: K (input width), N (output width padded to a multiple of 16), rows of the weight matrix
 __device__ constexpr int kK[5] = {32, 32, 48, 32, 32};
 __device__ constexpr int kN[5] = {32, 48, 32, 32, 32};
@@ -128,17 +129,24 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
   uint32_t phase = 0;
 
   // one layer: operands are staged; fence, issue, wait for the accumulator
+  // The layer input (this thread's row, tf32 hi / lo) goes straight to tensor memory (tcgen05.st) and is read from
+  // there by the ".ts" form of tcgen05.mma: no shared-memory staging (2 x 16-24 KB of stores per layer and tile) and
+  // no shared-memory operand fetch for A.  dbg bit 4 selects the shared-memory A path (kept for comparison).
+  const bool a_smem = (dbg & 16) != 0;
   auto run_layer = [&](int l) {
-    if (!(dbg & 8)) fence_async_smem();
+    if (a_smem) fence_async_smem();
     fence_before_sync();
     __syncthreads();
     if (dbg & 1) return;
     if (uwarp == 0) {
       if (elect_one()) {
         fence_after_sync();
-        if (!(dbg & 2))
+        if (a_smem)
           issue_gemm(tmem_base, 128, kN[l], a_hi_u, a_lo_u, kK[l], smem_u32(smem + field_w_hi(l)),
                      smem_u32(smem + field_w_lo(l)), kK[l], kK[l], false);
+        else if (!(dbg & 2))
+          issue_gemm_ts(tmem_base, kN[l], tmem_base + kFwdAHi, tmem_base + kFwdALo, smem_u32(smem + field_w_hi(l)),
+                        smem_u32(smem + field_w_lo(l)), kK[l], kK[l]);
         mma_commit(mbar);
       }
       __syncwarp();
@@ -148,6 +156,12 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     fence_after_sync();
   };
 
+  auto stage32 = [&](const float (&r)[32]) {
+    if (a_smem)
+      store_row_split<32>(a_hi, a_lo, t, r);
+    else
+      tmem_store_row_split<32>(tmem_base, warp, kFwdAHi, kFwdALo, 0, r);
+  };
   const int64_t tiles = (M + kRows - 1) / kRows;
   const int lane = t & 31;
   // The operand tiles double as bounce buffers for the coalesced row I/O while no MMA is reading them: a warp's 32
@@ -164,14 +178,14 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
     const int64_t rr = ok ? row : (M - 1);  // out-of-range rows compute on a valid row; only saved activations are stored
     // ---- mlp_geo layer 0: 32 -> 32, ReLU
     warp_bounce_to_rows(bounce_in, lane, xpf, v);
-    store_row_split<32>(a_hi, a_lo, t, v);
+    stage32(v);
     const int64_t ntile = tile + gridDim.x;
     if (ntile < tiles) warp_load_rows_coalesced(x, ntile * kRows + warp * 32, M, lane, xpf);
     run_layer(0);
     tmem_load_row<32>(tmem_base, warp, 0, v);
     const uint32_t m_h1 = relu_bias_mask(v, s_bias);
     if (train) store_col32(sv.h1, sv.ld, row, v);
-    store_row_split<32>(a_hi, a_lo, t, v);
+    stage32(v);
     // ---- mlp_geo layer 1: 32 -> 33 (sdf | embedding), no activation
     run_layer(1);
     float geo[48];
@@ -195,13 +209,16 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
         in48[32 + 4 * c + 2] = q.z;
         in48[32 + 4 * c + 3] = q.w;
       }
-      store_row_split<48>(a_hi, a_lo, t, in48);
+      if (a_smem)
+        store_row_split<48>(a_hi, a_lo, t, in48);
+      else
+        tmem_store_row_split<48>(tmem_base, warp, kFwdAHi, kFwdALo, 0, in48);
     }
     run_layer(2);
     tmem_load_row<32>(tmem_base, warp, 0, v);
     const uint32_t m_g1 = relu_bias_mask(v, s_bias + 2 * 48);
     if (train) store_col32(sv.g1, sv.ld, row, v);
-    store_row_split<32>(a_hi, a_lo, t, v);
+    stage32(v);
     // ---- mlp_feature layer 1: 32 -> 32, ReLU
     run_layer(3);
     tmem_load_row<32>(tmem_base, warp, 0, v);
@@ -212,7 +229,7 @@ __global__ void __launch_bounds__(kRows, 2) field_mlp_fwd_kernel(const __grid_co
       sv.masks[sv.ld + row] = m_g1;
       sv.masks[2 * sv.ld + row] = m_g2;
     }
-    store_row_split<32>(a_hi, a_lo, t, v);
+    stage32(v);
     // ---- mlp_feature layer 2: 32 -> 32, no activation; residual with the embedding
     run_layer(4);
     tmem_load_row<32>(tmem_base, warp, 0, v);
@@ -594,10 +611,9 @@ __global__ void __launch_bounds__(kRows, 1) field_mlp_bwd_kernel(const __grid_co
 //     a rank-1 update on the CUDA cores.  Every delta tile is then 32 columns wide and chunk-aligned;
 //   * global loads that are consumed layers later (x rows, SH basis, sdf / alpha terms, next tile's d feature rows) are
 //     issued at the top of the tile.
-// TMEM map (512 columns): four 48-column data-gradient accumulators (one per K step), the five weight-gradient
-// accumulators, and the data-gradient GEMM's A operand (delta as tf32 hi / lo).
+// TMEM map (512 columns): the 48-column data-gradient accumulator, the five weight-gradient accumulators, and the
+// data-gradient GEMM's A operand (delta as tf32 hi / lo).
 constexpr int kBwd2TmemCols = 512;
-constexpr int kDinStride = 48;
 __device__ constexpr int kDw2Col[5] = {192, 240, 288, 352, 400};  // TMEM column of each layer's dW (+db) accumulator
 __device__ constexpr int kDw2N[5] = {48, 48, 64, 48, 48};         // N of the weight-gradient GEMM (inputs + ones + pad)
 constexpr int kBwd2AHi = 448, kBwd2ALo = 480;
@@ -793,8 +809,8 @@ __global__ void __launch_bounds__(kRows * S + 32, 1) field_mlp_bwd_split_kernel(
           NRB_ITRACE();  // 0: all workers arrived
           fence_after_sync();
           if (!(dbg & 2))
-            issue_gemm_ts(tmem_base, kDinStride, kK[l], tmem_base + kBwd2AHi, tmem_base + kBwd2ALo,
-                          smem_u32(smem + field_w_hi(l)), smem_u32(smem + field_w_lo(l)), 32, 32);
+            issue_gemm_ts(tmem_base, kK[l], tmem_base + kBwd2AHi, tmem_base + kBwd2ALo, smem_u32(smem + field_w_hi(l)),
+                          smem_u32(smem + field_w_lo(l)), 32, 32);
           mma_commit(mbar_data);
           NRB_ITRACE();  // 1: dIn chain issued
           if (!(dbg & 1))
@@ -853,22 +869,13 @@ __global__ void __launch_bounds__(kRows * S + 32, 1) field_mlp_bwd_split_kernel(
       tmem_store_row_split<W>(tmem_base, warp, kBwd2AHi, kBwd2ALo, col0, v);
       store_part_transposed_bf16<W>(dt_hi(b), dt_mid(b), quarter, lane, v, col0);
     };
-    auto load_din = [&](float (&v)[W]) {  // sum of the per-K-step partial accumulators
-      tmem_load_cols<W>(tmem_base, warp, col0, v);
-#pragma unroll
-      for (int k = 1; k < 4; ++k) {
-        float p[W];
-        tmem_load_cols<W>(tmem_base, warp, k * kDinStride + col0, p);
-#pragma unroll
-        for (int j = 0; j < W; ++j) v[j] += p[j];
-      }
-    };
+    auto load_din = [&](float (&v)[W]) { tmem_load_cols<W>(tmem_base, warp, col0, v); };
     auto apply_mask = [&](uint32_t m, float (&v)[W]) {
 #pragma unroll
       for (int j = 0; j < W; ++j) v[j] = ((m >> (col0 + j)) & 1u) ? v[j] : 0.0f;
     };
 
-    const int64_t last_ray = (M - 1) / samples_per_ray;
+    const uint32_t last_ray = static_cast<uint32_t>((M - 1) / samples_per_ray);
     float4 pfa[NPF], pfb[NPF];  // two prefetch sets: every activation tile is requested two layers before its use
     float4 df[W / 4];  // this thread's share of the tile's d feature rows, loaded one tile ahead
     if (any) {
@@ -892,12 +899,18 @@ __global__ void __launch_bounds__(kRows * S + 32, 1) field_mlp_bwd_split_kernel(
       for (int q = 0; q < NSH; ++q) {
         const int e = t + q * T;
         const int k = (e & 7) + 8 * ((e >> 8) & 1), c = (e >> 3) & 31;
-        const int64_t ray0 = (row0 + 4 * c) / samples_per_ray;
-        const int rem = static_cast<int>((row0 + 4 * c) - ray0 * samples_per_ray);
+        const uint32_t s0 = static_cast<uint32_t>(row0) + 4u * c;  // first sample of the chunk (M < 2^31)
+        const uint32_t ray0 = s0 / static_cast<uint32_t>(samples_per_ray);
+        const uint32_t rem = s0 - ray0 * static_cast<uint32_t>(samples_per_ray);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int64_t ray = min(ray0 + (rem + i) / samples_per_ray, last_ray);
-          shv[q][i] = __ldg(in.sh + ray * 16 + k);
+          uint32_t ray = ray0;
+          if (samples_per_ray >= 4) {
+            ray += (rem + i >= static_cast<uint32_t>(samples_per_ray)) ? 1u : 0u;
+          } else {
+            ray += (rem + i) / static_cast<uint32_t>(samples_per_ray);
+          }
+          shv[q][i] = __ldg(in.sh + static_cast<int64_t>(min(ray, last_ray)) * 16 + k);
         }
       }
       const int64_t rc = ok ? row : (M - 1);
@@ -1274,7 +1287,7 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   static const int dbg = std::getenv("NRB_FIELD_BWD_DEBUG") ? std::atoi(std::getenv("NRB_FIELD_BWD_DEBUG")) : 0;
   // threads per row: 1 = the one-thread-per-row kernel, 2 / 4 = the column-split kernel
   static const int split = std::getenv("NRB_FIELD_BWD_SPLIT") ? std::atoi(std::getenv("NRB_FIELD_BWD_SPLIT")) : 4;
-  if (split == 2 || split == 4) {
+  if ((split == 2 || split == 4) && M < (int64_t{1} << 31)) {
     auto kern = split == 2 ? field_mlp_bwd_split_kernel<2> : field_mlp_bwd_split_kernel<4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwd2Smem::total);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
