@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kRayWarps * 32) alpha_composite_fwd_kernel(
     for (int c = lane; c < C; c += 32) {
       const float* f = feats + n * S * C + c;
       float s = 0.0f;
-#pragma unroll 4
+#pragma unroll 16
       for (int i = 0; i < S; ++i) s += s_w[i] * __ldg(f + static_cast<size_t>(i) * C);
       features[n * C + c] = s;
     }
@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(kRayWarps * 32) alpha_composite_bwd_kernel(
   const float* en = iv.ends + n * iv.row_stride;
   const float gd = ddepth != nullptr ? ddepth[n] : 0.0f;
   const int last = sky ? S - 1 : S;
-  // G_s = dL/dw'_s ; lanes own samples here: every lane walks its own contiguous feature row
+  // G_s = dL/dw'_s ; lanes own samples here: every lane walks its own contiguous feature row (a channel-major variant
+  // with coalesced rows and a transpose-reduce for the dot products was measured 35 % slower: 4x the instructions)
   for (int i = lane; i < S; i += 32) {
     float g = dweights != nullptr ? dweights[n * S + i] : 0.0f;
     if (i < last) g += gd * mul(add(st[i], en[i]), 0.5f);

@@ -79,6 +79,27 @@ def test_no_cpu_path():
         mlp(torch.rand((4, 4)))
 
 
+def test_losses_and_optimizer_have_no_cpu_path():
+    """SURVEY 8f next-1 / next-2 entry points: CPU tensors are refused, nothing falls back to torch."""
+    from types import SimpleNamespace
+
+    from neuradar_b200 import losses
+    from neuradar_b200.optim import FusedAdam, FusedAdamW
+
+    sb = torch.linspace(0, 1, 9).repeat(3, 1)
+    rs = SimpleNamespace(spacing_starts=sb[:, :-1, None], spacing_ends=sb[:, 1:, None])
+    w = torch.full((3, 8, 1), 0.1, requires_grad=True)
+    with pytest.raises(RuntimeError):
+        losses.distortion_loss([w], [rs])
+    with pytest.raises(RuntimeError):
+        losses.zipnerf_interlevel_loss([w, w], [rs, rs])
+    for cls in (FusedAdam, FusedAdamW):
+        with pytest.raises(ValueError):
+            cls([torch.nn.Parameter(torch.zeros(8))], lr=1e-2)
+    # the reference's sdist helper (losses.py:107-112) is plain indexing and works anywhere
+    assert torch.equal(losses.ray_samples_to_sdist(rs), sb)
+
+
 def test_product_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "neuradar_b200")
     for dirpath, _, files in os.walk(pkg):
