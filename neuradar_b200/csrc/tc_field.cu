@@ -1063,6 +1063,347 @@ __global__ void __launch_bounds__(kRows * S + 32, 1) field_mlp_bwd_split_kernel(
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Two tiles in flight per CTA.  The per-layer chain stage -> signal -> issue -> commit -> wake -> tcgen05.ld is serial
+// for one tile (clock64 trace: ~4 K cycles per layer with the SM mostly waiting), so this variant runs TWO independent
+// 128-sample tiles per CTA, each owned by a group of 8 warps (thread = 16 columns of a row), phase-shifted by
+// construction because one warp issues the tensor-core chains of both groups alternately.  Resources per group: one
+// delta^T / input^T operand buffer (the two buffers of the split kernel), 48 + 64 TMEM columns (data-gradient
+// accumulator, A operand); the five weight-gradient accumulators (256 columns) are shared: both groups' chains add into
+// them, issued by the same thread and therefore ordered.  While one group waits for its chain, the other stages.
+constexpr int kPairThreads = 2 * 256 + 96;  // two groups of 8 worker warps + three issuing warps
+constexpr int kPairDwCol0 = 96;  // dIn accumulators at 0 and 48, dW at 96 .. 351, A operands at 352 .. 479
+__device__ constexpr int kPairDwOff[5] = {0, 48, 96, 160, 208};
+constexpr int kPairACol0 = 352;
+
+struct FieldBwdPairSmem {
+  static constexpr int w1row0 = field_w_hi(5);
+  static constexpr int dt = w1row0 + 128;                // [2 groups][hi, mid] delta^T
+  static constexpr int at = dt + 4 * kDt16Bytes;         // [2 groups][hi, mid] [input | ones]^T
+  static constexpr int bounce = at + 4 * kAt16Bytes;     // 16 warps x 2 KB
+  static constexpr int mbar = bounce + 32768;            // data[2], dw[2], ready[2]
+  static constexpr int tmem = mbar + 48;
+  static constexpr int total = tmem + 16;
+};
+
+__global__ void __launch_bounds__(kPairThreads, 1) field_mlp_bwd_pair_kernel(const __grid_constant__ FieldParams prm,
+                                                                             const __grid_constant__ FieldBwdIn in,
+                                                                             const __grid_constant__ FieldBwdOut out,
+                                                                             int samples_per_ray, int64_t M, int dbg) {
+  constexpr int W = 16, T = 256, NPF = 4, NSH = 2;
+  extern __shared__ __align__(128) char smem[];
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const bool issuer = warp >= 16;            // warps 16 / 17: data-gradient chains of group 0 / 1, warp 18: weight-gradient chains
+  const int g = (warp >> 3) & 1;            // tile group
+  const int tg = t & 255;                    // thread index within the group
+  const int h = (warp >> 2) & 1, quarter = warp & 3, r = t & (kRows - 1), col0 = h * W;
+  char* dt_hi = smem + FieldBwdPairSmem::dt + (2 * g) * kDt16Bytes;
+  char* dt_mid = dt_hi + kDt16Bytes;
+  char* at_hi = smem + FieldBwdPairSmem::at + (2 * g) * kAt16Bytes;
+  char* at_mid = at_hi + kAt16Bytes;
+  float* w1row0 = reinterpret_cast<float*>(smem + FieldBwdPairSmem::w1row0);
+  uint64_t* mbar_data = reinterpret_cast<uint64_t*>(smem + FieldBwdPairSmem::mbar);  // [2]
+  uint64_t* mbar_dw = mbar_data + 2;                                                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + FieldBwdPairSmem::tmem);
+  char* bounce = smem + FieldBwdPairSmem::bounce + (warp & 15) * (32 * W * 4);
+
+  stage_weight_transposed_split(prm.w[0], 32, 32, 32, smem + field_w_hi(0), smem + field_w_lo(0));
+  stage_weight_transposed_split(prm.w[1] + 32, 32, 32, 32, smem + field_w_hi(1), smem + field_w_lo(1));
+  stage_weight_transposed_split(prm.w[2], 32, 32, 48, smem + field_w_hi(2), smem + field_w_lo(2));
+  stage_weight_transposed_split(prm.w[3], 32, 32, 32, smem + field_w_hi(3), smem + field_w_lo(3));
+  stage_weight_transposed_split(prm.w[4], 32, 32, 32, smem + field_w_hi(4), smem + field_w_lo(4));
+  if (t < 32) w1row0[t] = __ldg(prm.w[1] + t);
+  for (int e = t; e < (4 * kDt16Bytes + 4 * kAt16Bytes) / 16; e += kPairThreads)
+    reinterpret_cast<uint4*>(smem + FieldBwdPairSmem::dt)[e] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  // [ones, 0 x 7] rows of a group's input^T operand: rows 32..39 (32-input layers) and 48..55 (layer 2)
+  auto write_ones_rows = [&](char* hi_tile, char* mid_tile, int row_base, int first, int stride) {
+    for (int e = first; e < 8 * 16; e += stride) {
+      const uint32_t v = (e & 7) == 0 ? 0x3F803F80u : 0u;  // bf16 1.0 pairs
+      const uint32_t off = tile16_offset(row_base + (e & 7), e >> 3);
+      *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(v, v, v, v);
+      *reinterpret_cast<uint4*>(mid_tile + off) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  };
+  for (int b = 0; b < 2; ++b) {
+    char* hi_tile = smem + FieldBwdPairSmem::at + (2 * b) * kAt16Bytes;
+    write_ones_rows(hi_tile, hi_tile + kAt16Bytes, 32, t, kPairThreads);
+    write_ones_rows(hi_tile, hi_tile + kAt16Bytes, 48, t, kPairThreads);
+  }
+  if (warp == 0) tmem_alloc<kBwd2TmemCols>(tmem_slot);
+  if (t == 0)
+    for (int i = 0; i < 4; ++i) mbar_init(mbar_data + i, 1);
+  fence_async_smem();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+  const int64_t tiles = (M + kRows - 1) / kRows;
+  // tiles of this CTA: blockIdx.x + k * gridDim.x, k = 0, 1, ...; group g takes k = g, g + 2, ...
+  const int64_t mine = static_cast<int64_t>(blockIdx.x) < tiles ? (tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const bool any = mine > 0;
+
+  if (issuer) {
+    // Three issuing warps.  Warps 16 / 17 issue the data-gradient chain of group 0 / 1 as soon as THAT group has staged
+    // its operands (the group waits for it: nothing else sits on its critical path).  Warp 18 issues the weight-gradient
+    // chains of both groups in strict alternation: ONE thread issues everything that accumulates into the shared dW
+    // accumulators, so those accumulations are ordered.  (History: one issuer for everything 1.64 ms - it was busy
+    // ~60 % of the time; serving whichever group is ready first through polled mbarriers 1.81 ms - a spinning issuer
+    // steals issue slots; data / weight issuers 1.50 ms.)
+    if (warp < 18) {
+      const int gg = warp - 16;
+      int itrace = 1024;
+      for (int64_t k = gg; k < mine; k += 2) {
+#pragma unroll 1
+        for (int l = 4; l >= 0; --l) {
+          if (gg == 0)
+            asm volatile("bar.sync 1, %0;" ::"n"(T + 64) : "memory");
+          else
+            asm volatile("bar.sync 2, %0;" ::"n"(T + 64) : "memory");
+          if (elect_one()) {
+            if (gg == 0) NRB_ITRACE();
+            fence_after_sync();
+            const uint32_t a_col = tmem_base + kPairACol0 + 64 * gg;
+            issue_gemm_ts(tmem_base + 48 * gg, kK[l], a_col, a_col + 32, smem_u32(smem + field_w_hi(l)),
+                          smem_u32(smem + field_w_lo(l)), 32, 32);
+            mma_commit(mbar_data + gg);
+            if (gg == 0) NRB_ITRACE();
+          }
+          __syncwarp();
+        }
+      }
+    } else {
+      bool first = true;
+      for (int64_t k0 = 0; k0 < mine; k0 += 2) {
+#pragma unroll 1
+        for (int l = 4; l >= 0; --l) {
+#pragma unroll 1
+          for (int gg = 0; gg < 2; ++gg) {
+            if (k0 + gg >= mine) continue;
+            if (gg == 0)
+              asm volatile("bar.sync 1, %0;" ::"n"(T + 64) : "memory");
+            else
+              asm volatile("bar.sync 2, %0;" ::"n"(T + 64) : "memory");
+            if (elect_one()) {
+              fence_after_sync();
+              char* dth = smem + FieldBwdPairSmem::dt + (2 * gg) * kDt16Bytes;
+              char* ath = smem + FieldBwdPairSmem::at + (2 * gg) * kAt16Bytes;
+              issue_gemm_bf16_stacked(tmem_base + kPairDwCol0 + kPairDwOff[l], kDw2N[l], smem_u32(dth), smem_u32(ath),
+                                      smem_u32(ath + kAt16Bytes), !(first && gg == 0));
+              mma_commit(mbar_dw + gg);
+            }
+            __syncwarp();
+          }
+        }
+        first = false;
+      }
+    }
+  } else {
+    const float beta = fabsf(__ldg(prm.beta)) + prm.beta_min;
+    uint32_t phase_data = 0, phase_dw = 0;
+    bool dw_pending = false;
+    float dbeta_acc = 0.0f;
+    int trace_n = 0;
+    const uint32_t a_hi_col = kPairACol0 + 64 * g, a_lo_col = a_hi_col + 32, din_col = 48 * g;
+    const uint32_t last_ray = static_cast<uint32_t>((M - 1) / samples_per_ray);
+    auto signal_issuer = [&]() {
+      NRB_TRACE();  // staged
+      fence_async_smem();
+      fence_before_sync();
+      if (g == 0)
+        asm volatile("bar.arrive 1, %0;" ::"n"(T + 64) : "memory");
+      else
+        asm volatile("bar.arrive 2, %0;" ::"n"(T + 64) : "memory");
+      dw_pending = true;
+    };
+    auto wait_data = [&]() {
+      mbar_wait(mbar_data + g, phase_data);
+      phase_data ^= 1;
+      fence_after_sync();
+      NRB_TRACE();  // dIn done
+    };
+    auto wait_dw = [&]() {  // the chain that last read this group's operand buffer
+      NRB_TRACE();  // before wait_dw
+      if (dw_pending) {
+        mbar_wait(mbar_dw + g, phase_dw);
+        phase_dw ^= 1;
+        dw_pending = false;
+      }
+      NRB_TRACE();  // after wait_dw
+    };
+    auto prefetch_act = [&](const float* __restrict__ fm, int64_t row0, float4 (&pf)[NPF]) {
+#pragma unroll
+      for (int q = 0; q < NPF; ++q) {
+        const int e = tg + q * T;
+        const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        pf[q] = __ldg(reinterpret_cast<const float4*>(fm + j * in.ld + row0 + 4 * c));
+      }
+    };
+    auto commit_act = [&](const float4 (&pf)[NPF]) {  // rows 0..31 of input^T
+#pragma unroll
+      for (int q = 0; q < NPF; ++q) {
+        const int e = tg + q * T;
+        const int j = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        store_bf16x4(at_hi, at_mid, j, c, pf[q].x, pf[q].y, pf[q].z, pf[q].w);
+      }
+    };
+    auto stage_delta = [&](const float (&v)[W]) {
+      tmem_store_row_split<W>(tmem_base, warp, a_hi_col, a_lo_col, col0, v);
+      store_part_transposed_bf16<W>(dt_hi, dt_mid, quarter, lane, v, col0);
+    };
+    auto load_din = [&](float (&v)[W]) { tmem_load_cols<W>(tmem_base, warp, din_col + col0, v); };
+    auto apply_mask = [&](uint32_t m, float (&v)[W]) {
+#pragma unroll
+      for (int j = 0; j < W; ++j) v[j] = ((m >> (col0 + j)) & 1u) ? v[j] : 0.0f;
+    };
+
+    float4 pf[NPF];
+    for (int64_t k = g; k < mine; k += 2) {
+      const int64_t tile = blockIdx.x + k * gridDim.x;
+      const int64_t row0 = tile * kRows;
+      const int64_t row = row0 + r;
+      const bool ok = row < M;
+      const uint32_t m_h1 = __ldg(in.masks + row), m_g1 = __ldg(in.masks + in.ld + row), m_g2 = __ldg(in.masks + 2 * in.ld + row);
+      float delta[W], demb[W];
+      prefetch_act(in.g2, row0, pf);
+      {
+        float4 df[W / 4];
+        warp_load_part_coalesced<W>(in.dfeature, row0 + quarter * 32, M, col0, lane, df);
+        warp_bounce_part_to_rows<W>(bounce, lane, df, delta);
+      }
+#pragma unroll
+      for (int j = 0; j < W; ++j) {
+        delta[j] = ok ? delta[j] : 0.0f;
+        demb[j] = delta[j];  // residual branch
+      }
+      // ---- layer 4 (mlp_feature.layers.2): delta = d feature, input g2
+      wait_dw();
+      stage_delta(delta);
+      commit_act(pf);
+      write_ones_rows(at_hi, at_mid, 32, tg, T);
+      signal_issuer();
+      prefetch_act(in.g1, row0, pf);
+      wait_data();
+      load_din(delta);
+      apply_mask(m_g2, delta);
+      // ---- layer 3 (mlp_feature.layers.1): input g1
+      wait_dw();
+      stage_delta(delta);
+      commit_act(pf);
+      signal_issuer();
+      prefetch_act(in.emb, row0, pf);
+      float shv[NSH][4];  // the ray's SH basis for rows 32..47 of layer 2's input^T
+#pragma unroll
+      for (int q = 0; q < NSH; ++q) {
+        const int e = tg + q * T;
+        const int kk = (e & 7) + 8 * ((e >> 8) & 1), c = (e >> 3) & 31;
+        const uint32_t s0 = static_cast<uint32_t>(row0) + 4u * c;
+        const uint32_t ray0 = s0 / static_cast<uint32_t>(samples_per_ray);
+        const uint32_t rem = s0 - ray0 * static_cast<uint32_t>(samples_per_ray);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint32_t ray = ray0;
+          if (samples_per_ray >= 4) {
+            ray += (rem + i >= static_cast<uint32_t>(samples_per_ray)) ? 1u : 0u;
+          } else {
+            ray += (rem + i) / static_cast<uint32_t>(samples_per_ray);
+          }
+          shv[q][i] = __ldg(in.sh + static_cast<int64_t>(min(ray, last_ray)) * 16 + kk);
+        }
+      }
+      wait_data();
+      load_din(delta);
+      apply_mask(m_g1, delta);
+      // ---- layer 2 (mlp_feature.layers.0): input [emb | sh | 1]
+      wait_dw();
+      stage_delta(delta);
+      commit_act(pf);
+#pragma unroll
+      for (int q = 0; q < NSH; ++q) {
+        const int e = tg + q * T;
+        const int kk = (e & 7) + 8 * (e >> 8), c = (e >> 3) & 31;
+        store_bf16x4(at_hi, at_mid, 32 + kk, c, shv[q][0], shv[q][1], shv[q][2], shv[q][3]);
+      }
+      signal_issuer();
+      prefetch_act(in.h1, row0, pf);
+      const int64_t rc = ok ? row : (M - 1);
+      const float a_v = __ldg(in.alpha + rc), sd_v = __ldg(in.sdf + rc);
+      const float da_v = in.dalpha != nullptr ? __ldg(in.dalpha + rc) : 0.0f;
+      const float ds_v = in.dsdf != nullptr ? __ldg(in.dsdf + rc) : 0.0f;
+      wait_data();
+      load_din(delta);  // the SH part of the input carries no gradient
+#pragma unroll
+      for (int j = 0; j < W; ++j) demb[j] += delta[j];
+      // ---- layer 1 (mlp_geo.layers.1): delta = [d sdf | d emb]; input h1
+      float dsdf_v = 0.0f;
+      if (ok) {
+        const float sg = a_v * (1.0f - a_v);
+        dsdf_v = ds_v - da_v * beta * sg;
+        if (h == 0) dbeta_acc -= da_v * sd_v * sg;
+      }
+      wait_dw();
+      stage_delta(demb);  // accumulator rows 0..31 <-> W1 rows 1..32
+      if (h == 0) {       // accumulator row 32 <-> W1 row 0 (sdf)
+        const uint32_t hb = __float_as_uint(dsdf_v) & 0xFFFF0000u;
+        const __nv_bfloat16 mid = __float2bfloat16_rn(dsdf_v - __uint_as_float(hb));
+        const uint32_t off = tile16_offset(32, r >> 3) + (r & 7) * 2;
+        *reinterpret_cast<uint16_t*>(dt_hi + off) = static_cast<uint16_t>(hb >> 16);
+        *reinterpret_cast<__nv_bfloat16*>(dt_mid + off) = mid;
+      }
+      commit_act(pf);
+      write_ones_rows(at_hi, at_mid, 32, tg, T);  // rows 32..39 held SH values during layer 2
+      signal_issuer();
+      warp_load_part_coalesced<W>(in.x, row0 + quarter * 32, M, col0, lane, pf);  // x rows (layer 0's input)
+      wait_data();
+      load_din(delta);
+#pragma unroll
+      for (int j = 0; j < W; ++j) delta[j] = fmaf(dsdf_v, w1row0[col0 + j], delta[j]);
+      apply_mask(m_h1, delta);
+      // ---- layer 0 (mlp_geo.layers.0): input x (row-major in memory: transposed through registers)
+      {
+        float xrow[W];
+        warp_bounce_part_to_rows<W>(bounce, lane, pf, xrow);
+        wait_dw();
+        stage_delta(delta);
+        store_part_transposed_bf16<W>(at_hi, at_mid, quarter, lane, xrow, col0);
+      }
+      signal_issuer();
+      wait_data();
+      if (out.dx != nullptr) {
+        load_din(delta);
+        warp_store_part_coalesced<W>(out.dx, row0 + quarter * 32, M, col0, bounce, lane, delta);
+      }
+    }
+    wait_dw();
+    const float sb = warp_sum(dbeta_acc);
+    if (h == 0 && lane == 0 && out.dbeta != nullptr && sb != 0.0f) atomicAdd(out.dbeta, sb);
+  }
+  // ---- flush: weight and bias gradients from TMEM (group 0's first column group reads them)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (any && !issuer && g == 0 && h == 0) {
+    const int ar = r & 63;  // rows 0..63: hi part, 64..127: mid part of the same weight-gradient row
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+      float acc[64];
+      tmem_load_row<64>(tmem_base, warp, kPairDwCol0 + kPairDwOff[l], acc);
+      const int wrow = (l == 1) ? (ar == 32 ? 0 : ar + 1) : ar;
+      if (wrow < kOut[l] && ar <= 32) {
+        if (out.dw[l] != nullptr) {
+#pragma unroll
+          for (int kk = 0; kk < 48; ++kk)
+            if (kk < kK[l]) atomicAdd(out.dw[l] + wrow * kK[l] + kk, acc[kk]);
+        }
+        if (out.db[l] != nullptr) atomicAdd(out.db[l] + wrow, l == 2 ? acc[48] : acc[32]);
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_free<kBwd2TmemCols>(tmem_base);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Generic probe of descriptor conventions: P and Q are [128,32] row-major host-provided matrices staged as canonical
 // tiles; one chain of `ksteps` tf32 MMAs is issued with caller-chosen majors, M, N, LBO/SBO and per-step address
 // advances; the [128 lanes][32 columns] accumulator block is dumped.
@@ -1285,8 +1626,17 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
   static const int dbg = std::getenv("NRB_FIELD_BWD_DEBUG") ? std::atoi(std::getenv("NRB_FIELD_BWD_DEBUG")) : 0;
-  // threads per row: 1 = the one-thread-per-row kernel, 2 / 4 = the column-split kernel
-  static const int split = std::getenv("NRB_FIELD_BWD_SPLIT") ? std::atoi(std::getenv("NRB_FIELD_BWD_SPLIT")) : 4;
+  // 22 (default) = two tiles in flight per CTA; 2 / 4 = the column-split kernel with that many threads per row;
+  // 1 = the one-thread-per-row kernel
+  static const int split = std::getenv("NRB_FIELD_BWD_SPLIT") ? std::atoi(std::getenv("NRB_FIELD_BWD_SPLIT")) : 22;
+  if (split == 22 && M < (int64_t{1} << 31)) {  // two tiles in flight per CTA
+    e = cudaFuncSetAttribute(field_mlp_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwdPairSmem::total);
+    NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const unsigned pgrid = static_cast<unsigned>(std::min<int64_t>((tiles + 1) / 2, sm_count()));
+    field_mlp_bwd_pair_kernel<<<pgrid, kPairThreads, FieldBwdPairSmem::total, static_cast<cudaStream_t>(stream)>>>(
+        to_params(p), bi, bo, samples_per_ray, M, dbg);
+    return finish_launch("nrb_field_mlp_bwd");
+  }
   if ((split == 2 || split == 4) && M < (int64_t{1} << 31)) {
     auto kern = split == 2 ? field_mlp_bwd_split_kernel<2> : field_mlp_bwd_split_kernel<4>;
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwd2Smem::total);
