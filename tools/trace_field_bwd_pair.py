@@ -33,10 +33,9 @@ print("per layer l4..l0:  wait_dw | stage | signal->dIn done | dIn done->next wa
 nxt = np.concatenate([W[:, 1:, 0], np.full((W.shape[0], 1), np.nan)], axis=1)
 for name, v in (("wait_dw", W[:, :, 1] - W[:, :, 0]), ("stage", W[:, :, 2] - W[:, :, 1]), ("sig->dIn", W[:, :, 3] - W[:, :, 2]), ("dIn->next", nxt - W[:, :, 3])):
     print(f"{name:10s}", np.nanmedian(v, axis=0))
-# issuer: 3 stamps per (layer, group): 30 per tile pair
-I = it[: (len(it) // 30) * 30].reshape(-1, 5, 2, 3)[3:25]
-print("issuer: dIn issue", np.median(I[..., 1] - I[..., 0], axis=0).tolist())
-print("issuer: dW issue ", np.median(I[..., 2] - I[..., 1], axis=0).tolist())
-flat = I.reshape(I.shape[0], 10, 3)
-gap = flat[:, 1:, 0] - flat[:, :-1, 2]
-print("issuer: wait before next group-layer", np.median(gap, axis=0).tolist())
+# data issuer of group 0: 2 stamps per layer (all arrived, chain issued): 10 per tile
+I = it[: (len(it) // 10) * 10].reshape(-1, 5, 2)[3:40]
+print("data issuer g0: dIn issue per layer", np.median(I[..., 1] - I[..., 0], axis=0).tolist())
+sig = W[:, :, 2]
+print("thread0 staged -> all of the group arrived:", np.median(I[: len(sig), :, 0] - sig[: len(I)], axis=0).tolist())
+print("chain issued -> thread0 sees dIn done:", np.median(W[: len(I), :, 3] - I[: len(W), :, 1], axis=0).tolist())
