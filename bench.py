@@ -9,6 +9,13 @@ SURVEY.md 8d, gradients of every hash table and MLP) over one batch of synthetic
 its own rays (weak scaling, 65536 rays per GPU) and the step ends with ONE all-reduce of the flat gradient arena.
 Workload at N=1 = BASELINE.json configs[1]: 65536 mixed camera/lidar/radar rays, 16-level 2^19 main grid, 48
 samples per ray, proposal rounds of 64 and 48 samples on the 6-level 2^20 grid.  Prints ONE JSON line.
+
+  --optimizer      adds the fused Adam / AdamW update of SURVEY.md 8f next-2 to the step (both arms)
+  --regularisers   adds the interlevel + distortion losses of SURVEY.md 8f next-1 to the step (both arms)
+
+`roofline` = the kernel with the largest share of the step (`rooflines` has every major kernel): algorithmic bytes or
+FLOPs per launch / CUDA-event duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes per
+launch from the committed ncu capture (profiles/r1_traffic.json).
 """
 from __future__ import annotations
 
