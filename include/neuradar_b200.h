@@ -172,6 +172,53 @@ typedef struct {
 } nrb_field_bwd_out_t;
 int nrb_field_mlp_bwd(const nrb_field_mlp_t* mlp, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
                       int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
+/* ---- fused field: hash-grid gather + geometry MLP + feature MLP in one kernel, backward with recomputed activations
+ * (round 2; replaces the nrb_hash_fwd -> nrb_field_mlp_fwd pair and nrb_field_mlp_bwd -> nrb_hash_bwd on the training
+ * path: NeuRADHashEncoding.forward + NeuRADField.forward, neurad_encoding.py:152-189, neurad_field.py:128-152).
+ * Forward: pass EITHER `grid` with the contracted sample means xyz [M,3] and stds std [M] (or NULL) from
+ * nrb_frustum_gaussians - the 32 hash features (num_levels * features_per_level == 32, 2 or 4 features per level) are
+ * gathered inside the kernel and never written - OR the hash features x [M,32] (grid == NULL; scenes with actors).
+ * Outputs as nrb_field_mlp_fwd.  For training pass `saved`: ximg receives the bf16 hi / mid operand image of the hash
+ * features (nrb_field_fused_image_bytes(M) bytes: 16 KB per 128-sample tile) and masks [3][ld] one bit per ReLU unit of
+ * the three hidden layers, ld = nrb_field_saved_ld(M).  Nothing else is kept: the backward recomputes the activations. */
+typedef struct {
+  void* ximg;
+  uint32_t* masks;
+  int64_t ld;
+} nrb_field_fused_saved_t;
+int64_t nrb_field_fused_image_bytes(int64_t M);
+int nrb_field_fused_fwd(const nrb_field_mlp_t* mlp, const nrb_grid_t* grid, const float* xyz, const float* std,
+                        const float* x, const float* sh, int32_t samples_per_ray, int64_t M, float* feature, float* sdf,
+                        float* alpha, const nrb_field_fused_saved_t* saved, nrb_stream_t stream);
+/* Backward.  The gradient of the feature output is EITHER dfeature [M,32] OR - with the compositor folded in
+ * (sum_s w f, models/neuradar.py:509) - its factors dfeat_ray [rays,32] and weights [M]: dfeature[m] = weights[m] *
+ * dfeat_ray[m / samples_per_ray].  dsdf / dalpha [M] are optional.  dximg (optional) receives the gradient with
+ * respect to the hash features as a tile image: float4 element (tile, chunk c of 4 features, sample r of the tile) at
+ * [(tile * 8 + c) * 128 + r] (nrb_field_fused_image_bytes(M) * 1 bytes); nrb_hash_bwd_image scatters it into the table.
+ * Parameter gradients are ACCUMULATED as in nrb_field_mlp_bwd. */
+typedef struct {
+  nrb_field_fused_saved_t saved;
+  const float* sh;
+  const float* sdf;
+  const float* alpha;
+  const float* dfeature;
+  const float* dfeat_ray;
+  const float* weights;
+  const float* dsdf;
+  const float* dalpha;
+} nrb_field_fused_bwd_in_t;
+typedef struct {
+  float* dximg;
+  float* dweights[5];
+  float* dbiases[5];
+  float* dbeta;
+} nrb_field_fused_bwd_out_t;
+int nrb_field_fused_bwd(const nrb_field_mlp_t* mlp, const nrb_field_fused_bwd_in_t* in,
+                        const nrb_field_fused_bwd_out_t* out, int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
+/* nrb_hash_bwd for a data gradient in the tile-image layout above (32 features per sample). */
+int nrb_hash_bwd_image(const nrb_grid_t* grid, const float* x, const float* std, const float* dyimg, float* dtable,
+                       int64_t M, void* workspace, int64_t workspace_bytes, nrb_stream_t stream);
+
 /* Debug probe of the UMMA descriptor conventions: P, Q [128,32] are staged as canonical tiles, a chain of tf32 MMAs
  * is issued with cfg = {a_major, b_major, M, N, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps} (host ints) and the
  * [128 lanes][32 columns] accumulator block is written to dump. */

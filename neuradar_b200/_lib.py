@@ -92,6 +92,20 @@ class FieldBwdOut(C.Structure):
     _fields_ = [("dx", C.c_void_p), ("dweights", C.c_void_p * 5), ("dbiases", C.c_void_p * 5), ("dbeta", C.c_void_p)]
 
 
+class FieldFusedSaved(C.Structure):  # nrb_field_fused_saved_t
+    _fields_ = [("ximg", C.c_void_p), ("masks", C.c_void_p), ("ld", C.c_int64)]
+
+
+class FieldFusedBwdIn(C.Structure):
+    _fields_ = [("saved", FieldFusedSaved)] + [
+        (n, C.c_void_p) for n in ("sh", "sdf", "alpha", "dfeature", "dfeat_ray", "weights", "dsdf", "dalpha")
+    ]
+
+
+class FieldFusedBwdOut(C.Structure):
+    _fields_ = [("dximg", C.c_void_p), ("dweights", C.c_void_p * 5), ("dbiases", C.c_void_p * 5), ("dbeta", C.c_void_p)]
+
+
 class Spacing(C.Structure):
     _fields_ = [("lam", C.c_float), ("scaling", C.c_float)]
 
@@ -125,6 +139,11 @@ SIGNATURES = {
     "nrb_field_saved_ld": [_I64],
     "nrb_field_mlp_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldBwdIn), C.POINTER(FieldBwdOut), _I32, _I64, _P],
     "nrb_tc_probe": [_P, _P, C.POINTER(C.c_int32), _P, _P],
+    "nrb_field_fused_image_bytes": [_I64],
+    "nrb_field_fused_fwd": [C.POINTER(FieldMlp), C.POINTER(Grid), _P, _P, _P, _P, _I32, _I64, _P, _P, _P,
+                            C.POINTER(FieldFusedSaved), _P],
+    "nrb_field_fused_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldFusedBwdIn), C.POINTER(FieldFusedBwdOut), _I32, _I64, _P],
+    "nrb_hash_bwd_image": [C.POINTER(Grid), _P, _P, _P, _P, _I64, _P, _I64, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
     "nrb_pdf_sample": [C.POINTER(Rays), Spacing, _P, _P, _I32, _P, _P, _I32, _F, _F, _P, _P, _P, _P, _P],
     "nrb_density_weights_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],
@@ -140,7 +159,8 @@ SIGNATURES = {
     "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
     "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P, _I64, _P],
 }
-_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64, "nrb_field_saved_ld": C.c_int64}
+_RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64, "nrb_field_saved_ld": C.c_int64,
+             "nrb_field_fused_image_bytes": C.c_int64}
 
 _lib: Optional[C.CDLL] = None
 

@@ -1,12 +1,17 @@
 """Data parallelism of the hot path: rays are independent, so each rank processes its own contiguous slice of the
-global batch with replicated parameters, and the only exchange is ONE all-reduce over a flat gradient arena
+global batch with replicated parameters, and the only exchange is the all-reduce of a flat gradient arena
 (hash tables + MLP weights) per step.  Replaces the reference's DistributedDataParallel wrap with
 find_unused_parameters=True and 25 MiB buckets (nerfstudio/pipelines/base_pipeline.py:305-307): same result
-(sum / world_size), one NCCL call that NVSwitch can reduce in-network (NVLS).
+(sum / world_size), NCCL calls that NVSwitch can reduce in-network (NVLS).
+
+The arena is reduced in two pieces so that the collective hides behind compute: the main hash table's gradient (64 MiB
+of the 88 MiB at BASELINE config 2 / 3) is final as soon as the field's backward kernels are enqueued - autograd runs
+them BEFORE the two proposal rounds' backward - so its all-reduce starts right there on a communication stream and
+overlaps with the proposal backward; only the small remainder (proposal table + MLPs) is reduced after the last kernel.
 """
 from __future__ import annotations
 
-from typing import Iterable, List, Optional, Tuple
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -27,44 +32,128 @@ def shard_bounds(num_rays: int, world_size: int, rank: int, granule: int = 1) ->
     return start * granule, end * granule
 
 
+def _world(group=None) -> int:
+    if not dist.is_available() or not dist.is_initialized():
+        return 1
+    return dist.get_world_size(group)
+
+
+class OverlappedReduce:
+    """All-reduce of one flat gradient buffer whose first `n_early` elements become final early in the backward pass.
+
+    `start_early()` (called by the backward of the kernel that produced those gradients, on the stream it ran on) launches
+    their all-reduce on a side stream; `finish()` reduces the rest and joins.  Without an early call `finish()` reduces
+    everything in one collective.  Single process: no-ops."""
+
+    def __init__(self, flat: Tensor, n_early: int = 0):
+        self.flat, self.n_early = flat, int(n_early)
+        self._work = None
+        self._stream: Optional[torch.cuda.Stream] = None
+        self.group = None
+
+    def start_early(self) -> None:
+        if self.n_early <= 0 or self._work is not None or _world(self.group) == 1:
+            return
+        if self.flat.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=self.flat.device)
+            self._stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            with torch.cuda.stream(self._stream):
+                self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        else:
+            self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self, group=None) -> float:
+        """Sum over ranks; returns 1 / world_size (the caller applies the average or hands it to the optimiser)."""
+        world = _world(group)
+        if world == 1:
+            return 1.0
+        if self._work is not None:
+            dist.all_reduce(self.flat[self.n_early :], op=dist.ReduceOp.SUM, group=group)
+            self._work.wait()  # the current stream waits for the early collective
+            if self._stream is not None:
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._stream)
+            self._work = None
+        else:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        return 1.0 / world
+
+
+def order_early_first(params: Sequence[nn.Parameter], early: Optional[Iterable[nn.Parameter]]) -> Tuple[List[nn.Parameter], int]:
+    """Reorder `params` so that the `early` ones come first; returns (ordered, number of early parameters)."""
+    ids = {id(p) for p in (early or [])}
+    first = [p for p in params if id(p) in ids]
+    return first + [p for p in params if id(p) not in ids], len(first)
+
+
 class GradArena:
     """One contiguous fp32 buffer that holds the gradient of every trainable parameter as a view.
 
     `param.grad` is pointed into the arena, so autograd accumulates straight into it, `zero()` is one memset and
-    `all_reduce()` is one collective.  Parameters that receive no gradient in a step (e.g. the never-evaluated
-    first proposal field) simply contribute zeros, which is what DDP's find_unused_parameters does.
-    `direct_scatter=True` additionally lets the hash-grid backward kernels add straight into the arena
-    (functional.grad_sink_of) instead of returning a table-sized temporary to autograd."""
+    `all_reduce()` is one or two collectives (see OverlappedReduce).  Parameters that receive no gradient in a step
+    (e.g. the never-evaluated first proposal field) simply contribute zeros, which is what DDP's find_unused_parameters
+    does.  `direct_scatter=True` additionally lets the hash-grid backward kernels add straight into the arena
+    (functional.grad_sink_of) instead of returning a table-sized temporary to autograd.  `early` names the parameters
+    (hash tables with a direct sink) whose gradient is complete when their backward kernel has run.
+
+    Contract: gradients must stay views of the arena.  `optimizer.zero_grad()` / `module.zero_grad()` default to
+    set_to_none=True and would detach them; `zero()` and `all_reduce()` therefore re-link (`relink()`): a gradient that
+    was replaced is copied back into its view, one that was set to None is treated as zero."""
 
     def __init__(self, params: Iterable[nn.Parameter], skip_unused: Optional[List[nn.Parameter]] = None,
-                 direct_scatter: bool = False):
+                 direct_scatter: bool = False, early: Optional[Iterable[nn.Parameter]] = None):
         skip = {id(p) for p in (skip_unused or [])}
-        self.params = [p for p in params if p.requires_grad and id(p) not in skip]
-        if not self.params:
+        params = [p for p in params if p.requires_grad and id(p) not in skip]
+        if not params:
             raise ValueError("no trainable parameters")
+        self.params, n_first = order_early_first(params, early if direct_scatter else None)
         dev, total = self.params[0].device, 0
-        offsets = []
-        for p in self.params:
+        self.offsets = []
+        n_early = 0
+        for i, p in enumerate(self.params):
             if p.dtype != torch.float32 or p.device != dev:
                 raise ValueError("GradArena expects fp32 parameters on one device")
-            offsets.append(total)
+            self.offsets.append(total)
             total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned for the vector atomics
+            if i < n_first:
+                n_early = total
         self.flat = torch.zeros((total,), device=dev, dtype=torch.float32)
-        for p, off in zip(self.params, offsets):
-            p.grad = self.flat[off : off + p.numel()].view_as(p)
+        self.direct_scatter = direct_scatter
+        self.reducer = OverlappedReduce(self.flat, n_early)
+        self._views = [self.flat[off : off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
+        for i, (p, view) in enumerate(zip(self.params, self._views)):
+            p.grad = view
             if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
-                p._nrb_grad_sink = p.grad  # hash tables: the scatter kernels add straight into the arena
+                p._nrb_grad_sink = view  # hash tables: the scatter kernels add straight into the arena
+                if i < n_first:
+                    p._nrb_grad_ready = self.reducer.start_early
 
     @property
     def nbytes(self) -> int:
         return self.flat.numel() * 4
 
+    def relink(self) -> int:
+        """Point every `param.grad` back into the arena; returns how many had been detached."""
+        fixed = 0
+        for p, view in zip(self.params, self._views):
+            if p.grad is not None and p.grad.data_ptr() == view.data_ptr():
+                continue
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            if getattr(p, "_nrb_grad_sink", None) is not None:
+                p._nrb_grad_sink = view
+            fixed += 1
+        return fixed
+
     def zero(self) -> None:
         self.flat.zero_()
+        for p, view in zip(self.params, self._views):  # after the memset a detached gradient simply counts as zero
+            if p.grad is None or p.grad.data_ptr() != view.data_ptr():
+                p.grad = view
 
     def all_reduce(self, group=None, average: bool = True) -> None:
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        if average:
-            self.flat.mul_(1.0 / dist.get_world_size(group))
+        self.relink()
+        mult = self.reducer.finish(group)
+        if average and mult != 1.0:
+            self.flat.mul_(mult)

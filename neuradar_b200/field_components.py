@@ -13,6 +13,7 @@ implementation here: the CUDA kernels.
 """
 from __future__ import annotations
 
+import contextlib
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Set, Tuple, Type
 
@@ -365,7 +366,8 @@ class NeuRADHashEncoding(nn.Module):
         """Overwrite the features (and directions) of the samples that fall into an actor box
         (neurad_encoding.py:176-229,295-316).  mean [N,S,3], std [N,S,1] in world units."""
         n, s, _ = mean.shape
-        grad_ctx = torch.enable_grad() if self.config.require_actor_grad else torch.no_grad()
+        # the reference keeps the ambient grad mode when the actor poses are trainable (neurad_encoding.py:177)
+        grad_ctx = contextlib.nullcontext() if self.config.require_actor_grad else torch.no_grad()
         with grad_ctx:
             boxes2world, valid = self.actors.get_boxes2world(times, flatten=False)
             world2boxes = _pose_inverse(boxes2world)

@@ -113,8 +113,23 @@ class NeuRADField(nn.Module):
     with the next chunk's tensor-core MLP backward.  Measured on B200 (config 2): 11.97 ms/step unchunked, 11.71 ms
     with 2 chunks, 12.9 ms with 4 (per-chunk workspace clears and folds eat the overlap) - left off."""
 
+    fused = os.environ.get("NRB_FIELD_FUSED", "1") != "0"
+    """One kernel for hash gather + both MLPs, backward with recomputed activations (csrc/field_fused.cu).  0 selects
+    the round-1 kernel chain (nrb_hash_fwd -> nrb_field_mlp_fwd, saved activations) for A/B measurements."""
+
     def _field_chunk(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         """hash encode + everything after it (ONE tcgen05 kernel forward, one backward) for a set of rays."""
+        geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
+        weights = [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight]
+        biases = [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias]
+        beta, beta_min = self.sdf_to_density.beta, float(self.sdf_to_density.beta_min)
+        grid = self.hashgrid.static_grid
+        with_actors = self.hashgrid.has_actors and times is not None
+        if self.fused and not with_actors and grid.features_per_level in (2, 4):
+            # the 32 hash features are gathered inside the MLP kernel and never reach HBM
+            x3, std = F.frustum_gaussians(rays, iv, self.hashgrid.static_scale)
+            sh = self.direction_encoding(get_normalized_directions(rays.directions))
+            return F.field_fused(grid.hash_table, None, x3, std, sh, iv.num_samples, grid.spec, weights, biases, beta, beta_min)
         features, sample_dirs = self.hashgrid.encode_samples(rays, iv, times)
         if sample_dirs is None:  # directions are per ray: 16 SH values per ray, indexed by row / S in the kernel
             sh = self.direction_encoding(get_normalized_directions(rays.directions))
@@ -122,13 +137,9 @@ class NeuRADField(nn.Module):
         else:  # some samples were rotated into an actor frame: one SH row per sample
             sh = self.direction_encoding(get_normalized_directions(sample_dirs.reshape(-1, 3)))
             sh_group = 1
-        geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
-        return F.field_mlp(
-            features, sh, sh_group,
-            [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight],
-            [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias],
-            self.sdf_to_density.beta, float(self.sdf_to_density.beta_min),
-        )
+        if self.fused:
+            return F.field_fused(None, features, None, None, sh, sh_group, None, weights, biases, beta, beta_min)
+        return F.field_mlp(features, sh, sh_group, weights, biases, beta, beta_min)
 
     def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         N = rays.num_rays

@@ -175,6 +175,23 @@ def grad_sink_of(table: Tensor) -> Optional[Tensor]:
     return sink
 
 
+def _sink_written(table: Tensor) -> None:
+    """Called by a backward that added straight into a gradient sink (no tensor is returned to autograd for it, so
+    autograd's own stream bookkeeping does not cover the write).  (1) If the backward ran on a side stream - autograd
+    replays a node on the stream its forward ran on - the default stream is made to wait for it, so that an all-reduce
+    or optimiser step issued after `loss.backward()` cannot race with the scatter.  (2) The owner of the sink may have
+    registered a callback (dist.OverlappedReduce.start_early) to start reducing this gradient right away."""
+    dev = table.device
+    cur, main = torch.cuda.current_stream(dev), torch.cuda.default_stream(dev)
+    if cur != main:
+        ev = torch.cuda.Event()
+        ev.record(cur)
+        main.wait_event(ev)
+    ready = getattr(table, "_nrb_grad_ready", None)
+    if ready is not None:
+        ready()
+
+
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
@@ -205,6 +222,8 @@ class _HashEncode(torch.autograd.Function):
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), x.shape[0])), x.device)
         _lib.call("nrb_hash_bwd", C.byref(g), ptr(x), ptr(std), ptr(dy), ptr(dtable), ptr(dx), x.shape[0], ws, ws_bytes,
                   stream_ptr(), tag="nrb_hash_bwd:" + spec.tag)
+        if ctx.sink is not None:
+            _sink_written(table)
         return dx, (None if ctx.sink is not None else dtable), None, None, None
 
 
@@ -434,6 +453,118 @@ def field_mlp(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Ten
               beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
     """NeuRADField after the hash grid, fused on the tensor cores: (feature [M,32], sdf [M], alpha [M])."""
     return _FieldMlp.apply(x, sh, samples_per_ray, beta_min, beta, *weights, *biases)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused field: hash gather + both MLPs in one kernel; backward recomputes the activations
+# ------------------------------------------------------------------------------------------------
+def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf, dalpha):
+    """Shared by the two autograd Functions that end in the fused field kernel.  Returns (dx or None, dbeta, dws, dbs);
+    in gather mode the hash-table gradient is scattered here (into the direct sink or a fresh tensor kept on ctx)."""
+    table, x3, std, ximg, masks, sh, beta, sdf, alpha = saved_tensors[:9]
+    weights_ = list(saved_tensors[9:14])
+    rest = list(saved_tensors[14:])
+    biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+    M, dev = sdf.shape[0], sdf.device
+    need_dx = ctx.gather or ctx.needs_x_grad
+    dximg = torch.empty((int(_lib_().nrb_field_fused_image_bytes(M)) // 4,), device=dev, dtype=torch.float32) if need_dx else None
+    dws = [torch.zeros_like(w) for w in weights_]
+    dbs = [None if b is None else torch.zeros_like(b) for b in biases]
+    dbeta_eff = torch.zeros((1,), device=dev, dtype=torch.float32)
+    m = _field_struct(weights_, biases, beta, ctx.beta_min)
+    bi = _lib.FieldFusedBwdIn()
+    bi.saved.ximg, bi.saved.masks, bi.saved.ld = ptr(ximg), ptr(masks), masks.shape[1]
+    bi.sh, bi.sdf, bi.alpha = ptr(sh), ptr(sdf), ptr(alpha)
+    bi.dfeature, bi.dfeat_ray, bi.weights = ptr(dfeature), ptr(dfeat_ray), ptr(weights)
+    bi.dsdf, bi.dalpha = ptr(dsdf), ptr(dalpha)
+    bo = _lib.FieldFusedBwdOut()
+    bo.dximg = ptr(dximg)
+    for i in range(5):
+        bo.dweights[i] = ptr(dws[i])
+        bo.dbiases[i] = ptr(dbs[i])
+    bo.dbeta = ptr(dbeta_eff)
+    _lib.call("nrb_field_fused_bwd", C.byref(m), C.byref(bi), C.byref(bo), ctx.samples_per_ray, M, stream_ptr())
+    dx = dtable = None
+    if ctx.gather:
+        spec = ctx.spec
+        dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
+        g = spec.struct(table)
+        ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), M)), dev)
+        _lib.call("nrb_hash_bwd_image", C.byref(g), ptr(x3), ptr(std), ptr(dximg), ptr(dtable), M, ws, ws_bytes, stream_ptr(),
+                  tag="nrb_hash_bwd:" + spec.tag)
+        if ctx.sink is not None:
+            _sink_written(table)
+            dtable = None
+    elif ctx.needs_x_grad:
+        dx = dximg.view(-1, 8, 128, 4).permute(0, 2, 1, 3).reshape(-1, 32)[:M]
+    dbeta = (dbeta_eff * torch.sign(beta)).view_as(beta)  # d(|beta| + beta_min) / d beta
+    return dx, dtable, dbeta, dws, dbs
+
+
+def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train):
+    """Launch nrb_field_fused_fwd and stash what the backward needs on ctx.  Returns (feature, sdf, alpha)."""
+    gather = table is not None
+    sh, beta = f32c(sh.detach()), f32c(beta)
+    weights = [f32c(w) for w in params[:5]]
+    biases = [None if b is None else f32c(b) for b in params[5:]]
+    if gather:
+        table, x3 = f32c(table), f32c(x3)
+        std = None if std is None else f32c(std.reshape(-1))
+        M, dev = x3.shape[0], x3.device
+        g = spec.struct(table)
+    else:
+        x = f32c(x)
+        M, dev = x.shape[0], x.device
+    feature = torch.empty((M, 32), device=dev, dtype=torch.float32)
+    sdf = torch.empty((M,), device=dev, dtype=torch.float32)
+    alpha = torch.empty((M,), device=dev, dtype=torch.float32)
+    sv = _lib.FieldFusedSaved()
+    ximg = masks = None
+    if train:
+        ximg = torch.empty((int(_lib_().nrb_field_fused_image_bytes(M)),), device=dev, dtype=torch.uint8)
+        masks = torch.empty((3, int(_lib_().nrb_field_saved_ld(M))), device=dev, dtype=torch.int32)
+        sv.ximg, sv.masks, sv.ld = ptr(ximg), ptr(masks), masks.shape[1]
+    m = _field_struct(weights, biases, beta, beta_min)
+    _lib.call("nrb_field_fused_fwd", C.byref(m), C.byref(g) if gather else None, ptr(x3) if gather else None,
+              ptr(std) if gather else None, None if gather else ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature),
+              ptr(sdf), ptr(alpha), C.byref(sv), stream_ptr())
+    if train:
+        ctx.save_for_backward(table if gather else None, x3 if gather else None, std if gather else None, ximg, masks, sh,
+                              beta, sdf, alpha, *weights, *[b for b in biases if b is not None])
+        ctx.has_bias = [b is not None for b in biases]
+        ctx.samples_per_ray, ctx.beta_min, ctx.gather, ctx.spec = int(samples_per_ray), float(beta_min), gather, spec
+    return feature, sdf, alpha
+
+
+class _FieldFused(torch.autograd.Function):
+    """NeuRADField on (table, sample means x3 [M,3], stds [M]) or on given hash features x [M,32]: one forward kernel,
+    one backward kernel (+ the table scatter).  Outputs feature [M,32], sdf [M], alpha [M]."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, table, x, x3, std, sh, samples_per_ray: int, beta_min: float, spec, beta, *params):
+        ctx.sink = grad_sink_of(table) if table is not None else None
+        train = any(ctx.needs_input_grad)
+        ctx.needs_x_grad = x is not None and ctx.needs_input_grad[1]
+        return _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train)
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dfeature, dsdf, dalpha):
+        M = ctx.saved_tensors[7].shape[0]
+        dev = ctx.saved_tensors[7].device
+        dfeature = torch.zeros((M, 32), device=dev) if dfeature is None else f32c(dfeature)
+        dsdf = None if dsdf is None else f32c(dsdf)
+        dalpha = None if dalpha is None else f32c(dalpha)
+        dx, dtable, dbeta, dws, dbs = _field_fused_backward(ctx, ctx.saved_tensors, dfeature, None, None, dsdf, dalpha)
+        return (dtable, dx, None, None, None, None, None, None, dbeta, *dws, *dbs)
+
+
+def field_fused(table: Optional[Tensor], x: Optional[Tensor], x3: Optional[Tensor], std: Optional[Tensor], sh: Tensor,
+                samples_per_ray: int, spec: Optional[GridSpec], weights: Sequence[Tensor],
+                biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
+    """Fused field.  Gather mode: `table` + sample means `x3` [M,3] + `std` [M]; otherwise hash features `x` [M,32]."""
+    return _FieldFused.apply(table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, *weights, *biases)
 
 
 def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:
@@ -677,6 +808,8 @@ class _ProposalRound(torch.autograd.Function):
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), n_pts)), table.device)
         _lib.call("nrb_proposal_bwd", C.byref(r), C.byref(g), ptr(dec), ctx.scale, C.byref(i), ptr(feats), ptr(pre),
                   ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, stream_ptr())
+        if ctx.sink is not None:
+            _sink_written(table)
         return (None if ctx.sink is not None else dtable), ddec.reshape(ctx.dec_shape), None, None, None, None
 
 

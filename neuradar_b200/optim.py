@@ -18,6 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import AdamCfg, ptr, stream_ptr
+from .dist import OverlappedReduce, order_early_first
 
 import ctypes as C
 
@@ -25,21 +26,26 @@ import ctypes as C
 class _FlatGroup:
     """Parameters of one group re-homed into one flat buffer; .grad of each is a view of the flat gradient."""
 
-    def __init__(self, params: List[torch.nn.Parameter], direct_scatter: bool = False):
+    def __init__(self, params: List[torch.nn.Parameter], direct_scatter: bool = False, early=None):
+        params, n_first = order_early_first(params, early if direct_scatter else None)
         dev = params[0].device
-        offsets, total = [], 0
-        for p in params:
+        offsets, total, n_early = [], 0, 0
+        for i, p in enumerate(params):
             if p.dtype != torch.float32 or p.device != dev or not p.is_cuda:
                 raise ValueError("FusedAdam expects fp32 CUDA parameters on one device (there is no CPU path)")
             offsets.append(total)
             total += (p.numel() + 3) // 4 * 4  # 16-byte aligned views (vector atomics of the scatter kernels)
+            if i < n_first:
+                n_early = total
         self.params, self.offsets, self.numel = params, offsets, total
         self.p = torch.zeros((total,), device=dev, dtype=torch.float32)
         self.g = torch.zeros_like(self.p)
         self.m = torch.zeros_like(self.p)
-        self.v = torch.zeros_like(self.p)
+        self.v = torch.ones_like(self.p)  # padding lanes keep v = 1 so that eps = 0 cannot make them 0 / 0
         self.skipped = torch.zeros((1,), device=dev, dtype=torch.float32)  # steps GradScaler skipped (found_inf)
-        for p, off in zip(params, offsets):
+        self.reducer = OverlappedReduce(self.g, n_early)
+        for i, (p, off) in enumerate(zip(params, offsets)):
+            self.v[off : off + p.numel()].zero_()
             view = self.p[off : off + p.numel()].view_as(p)
             view.copy_(p.data)
             p.data = view
@@ -49,6 +55,8 @@ class _FlatGroup:
             p.grad = gview
             if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
                 p._nrb_grad_sink = gview  # hash tables: the scatter kernels add straight into the flat gradient
+                if i < n_first:
+                    p._nrb_grad_ready = self.reducer.start_early
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -58,14 +66,14 @@ class FusedAdam(torch.optim.Optimizer):
     _step_supports_amp_scaling = True  # GradScaler hands us grad_scale / found_inf instead of unscaling itself
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 direct_scatter: bool = False):
+                 direct_scatter: bool = False, early=None):
         if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
             raise ValueError("invalid Adam hyper-parameters")
         super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
         self._flat: List[_FlatGroup] = []
         for group in self.param_groups:
             ps = [p for p in group["params"] if p.requires_grad]
-            self._flat.append(_FlatGroup(ps, direct_scatter))
+            self._flat.append(_FlatGroup(ps, direct_scatter, early))
             group["step"] = 0
         # GradScaler.step sets (and deletes) self.grad_scale / self.found_inf around step(); they must not pre-exist
 
@@ -82,11 +90,10 @@ class FusedAdam(torch.optim.Optimizer):
 
     def all_reduce_grads(self, group=None) -> float:
         """Sum gradients over ranks; returns the multiplier (1 / world_size) for step(grad_mult=...)."""
-        if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
-            return 1.0
-        for f in self._flat:
-            dist.all_reduce(f.g, op=dist.ReduceOp.SUM, group=group)
-        return 1.0 / dist.get_world_size(group)
+        mult = 1.0
+        for f in self._flat:  # gradients flagged `early` may already be in flight (dist.OverlappedReduce)
+            mult = f.reducer.finish(group)
+        return mult
 
     def check_finite(self, found_inf: Optional[Tensor] = None) -> Tensor:
         """Device flag (1.0 if any gradient is inf / nan), like GradScaler's per-optimizer found_inf."""
@@ -104,7 +111,12 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         scale, found = getattr(self, "grad_scale", None), getattr(self, "found_inf", None)
         for group, f in zip(self.param_groups, self._flat):
-            for p, off in zip(f.params, f.offsets):  # someone replaced .grad (e.g. zero_grad(set_to_none=True))
+            for p, off in zip(f.params, f.offsets):
+                if p.data_ptr() != f.p.data_ptr() + 4 * off:  # model.to() / .float() / p.data = ... detached it
+                    view = f.p[off : off + p.numel()].view_as(p)
+                    view.copy_(p.data)
+                    p.data = view
+                # someone replaced .grad (e.g. zero_grad(set_to_none=True))
                 if p.grad is None or p.grad.data_ptr() != f.g.data_ptr() + 4 * off:
                     gview = f.g[off : off + p.numel()].view_as(p)
                     if p.grad is not None:
@@ -129,11 +141,14 @@ class FusedAdam(torch.optim.Optimizer):
         groups = []
         for group, f in zip(self.param_groups, self._flat):
             ids = []
-            for p, off in zip(f.params, f.offsets):
-                n = p.numel()
-                state[idx] = {"step": torch.tensor(float(group["step"])) - f.skipped.cpu()[0],
-                              "exp_avg": f.m[off : off + n].view_as(p).clone(),
-                              "exp_avg_sq": f.v[off : off + n].view_as(p).clone()}
+            where = {id(p): off for p, off in zip(f.params, f.offsets)}
+            for p in group["params"]:  # torch numbers EVERY parameter of the group, trainable or not
+                off = where.get(id(p))
+                if off is not None:
+                    n = p.numel()
+                    state[idx] = {"step": torch.tensor(float(group["step"])) - f.skipped.cpu()[0],
+                                  "exp_avg": f.m[off : off + n].view_as(p).clone(),
+                                  "exp_avg_sq": f.v[off : off + n].view_as(p).clone()}
                 ids.append(idx)
                 idx += 1
             groups.append({**{k: v for k, v in group.items() if k != "params"}, "params": ids})
@@ -145,9 +160,11 @@ class FusedAdam(torch.optim.Optimizer):
             for k, v in saved.items():
                 if k != "params":
                     group[k] = v
-            for p, off in zip(f.params, f.offsets):
+            where = {id(p): off for p, off in zip(f.params, f.offsets)}
+            for p in group["params"]:
+                off = where.get(id(p))
                 st = sd["state"].get(idx)
-                if st is not None:
+                if st is not None and off is not None:
                     n = p.numel()
                     f.m[off : off + n].view_as(p).copy_(st["exp_avg"])
                     f.v[off : off + n].view_as(p).copy_(st["exp_avg_sq"])
@@ -162,5 +179,6 @@ class FusedAdamW(FusedAdam):
     _decoupled = True
 
     def __init__(self, params, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 1e-2,
-                 direct_scatter: bool = False):
-        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, direct_scatter=direct_scatter)
+                 direct_scatter: bool = False, early=None):
+        super().__init__(params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, direct_scatter=direct_scatter,
+                         early=early)
