@@ -1,21 +1,29 @@
 #!/usr/bin/env python
 """Benchmark of the NeuRadar per-ray hot path (BASELINE.json: train-step rays/sec at 1/2/4/8 B200).
 
-  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+  python bench.py --gpus N --steps K --warmup W [--config C]     # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...        # the reference's own torch path on the host CPU
 
-A step = one fwd+bwd pass of the hot path (proposal sampling -> hash encode -> MLPs -> compositing, loss of
-SURVEY.md 8d, gradients of every hash table and MLP) over one batch of synthetic rays; for N > 1 each rank owns
-its own rays (weak scaling, 65536 rays per GPU) and the step ends with ONE all-reduce of the flat gradient arena.
-Workload at N=1 = BASELINE.json configs[1]: 65536 mixed camera/lidar/radar rays, 16-level 2^19 main grid, 48
-samples per ray, proposal rounds of 64 and 48 samples on the 6-level 2^20 grid.  Prints ONE JSON line.
+A step = one pass of the hot path (proposal sampling -> hash encode -> MLPs -> compositing; training configs add the
+loss of SURVEY.md 8d, the backward pass and the gradient all-reduce) over one batch of synthetic rays.  `--config`
+selects a BASELINE.json configuration (default 2: 65536 mixed camera/lidar/radar rays per GPU, 16-level 2^19 main
+grid, 48 samples per ray, proposal rounds of 64 and 48 samples on the 6-level 2^20 grid):
+    1  4096 radar rays (the reference's CPU-runnable case)          4  large scene: 2^22 tables, 128 samples, 16 actors
+    3  the 8-GPU shard of the 262144-ray step: 32768 rays per GPU   5  inference sweep: 1 M radar rays, chunks of 32768
+For N > 1 each rank owns its own rays (weak scaling) and the step ends with the all-reduce of the flat gradient arena:
+the main table's 64 MiB start reducing as soon as the field's backward is enqueued, hidden behind the proposal rounds'.
+The step is captured ONCE in a CUDA graph (fwd + bwd + collectives) and replayed; the timed loop rotates through four
+resident ray batches.  Prints ONE JSON line.
 
-  --optimizer      adds the fused Adam / AdamW update of SURVEY.md 8f next-2 to the step (both arms)
-  --regularisers   adds the interlevel + distortion losses of SURVEY.md 8f next-1 to the step (both arms)
+  --optimizer      adds the fused Adam / AdamW update to the step of both arms
+  --regularisers   adds the interlevel + distortion losses to the step of both arms
+  --no-graph       launch the step eagerly (what a plain training loop does)
 
 `roofline` = the kernel with the largest share of the step (`rooflines` has every major kernel): algorithmic bytes or
 FLOPs per launch / CUDA-event duration, against MEASURED_PEAKS.json; `traffic` = DRAM bytes per
-launch from the committed ncu capture (profiles/r1_traffic.json).
+launch from the committed ncu capture (profiles/r2_traffic.json).  `path_roofline` = the whole step against the HBM
+roofline of SURVEY.md 8d (algorithmic bytes per ray).  `parity_at_config` = the CUDA path against the reference's torch
+path on 4096 of the benchmark's own rays with the benchmark's own tables.
 """
 from __future__ import annotations
 
@@ -34,11 +42,7 @@ import torch  # noqa: E402
 
 METRIC = "train_step_rays_per_sec"
 UNIT = "rays/s"
-RAYS_PER_GPU = 65536
-PROP_SAMPLES = (64, 48)
-NERF_SAMPLES = 48
-WORKLOAD = ("config2: 65536 mixed camera/lidar/radar rays per GPU, main grid L16/F2/T2^19 (res 16..1024), "
-            "proposals (64,48) on L6/F1/T2^20, 48 samples/ray, fwd+bwd")
+N_BATCHES = 4
 
 
 def load_peaks():
@@ -80,7 +84,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
@@ -102,16 +106,35 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, regularisers: bool = False,
+# reference arm / CPU baseline: the reference's own torch path (oracle/_ref, materialised by oracle/build_ref.py), or the
+# oracle port of it when the reference modules are not there
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(w, sample: int, steps: int, warmup: int, seed: int = 42, regularisers: bool = False,
                       optimizer: bool = False):
-    """fwd+bwd of the reference algorithm (CPU oracle port, fp32 torch ops) on `num_rays` rays of the workload."""
+    """fwd(+bwd) of the reference algorithm on `sample` rays of workload `w` on the host CPU.
+    Returns (rays/s, ms/step, threads, kind, cpu model)."""
+    from neuradar_b200.synthetic import scaled_pixel_area, synthetic_rays
+    from oracle import ref_runner as R
+
+    rays = synthetic_rays(sample, seed=seed, mix=w.mix)
+    pa = scaled_pixel_area(rays)
+    if R.available() and not regularisers and not optimizer:
+        path = R.ReferencePath(main=w.main, prop_log2=w.prop_log2, proposal_samples=w.proposal_samples,
+                               nerf_samples=w.nerf_samples, seed=seed)
+        value, ms, cores = R.time_reference(rays, pa, path, steps, warmup, train=w.train)
+        return value, ms, cores, "reference", R.cpu_model_name()
+    value, ms, cores = cpu_port_run(w, rays, pa, steps, warmup, seed, regularisers, optimizer)
+    return value, ms, cores, "port", R.cpu_model_name()
+
+
+def cpu_port_run(w, rays, pa, steps, warmup, seed, regularisers, optimizer):
     from oracle import neuradar_oracle as O
-    from tests.parity_utils import scaled_pixel_area, synthetic_rays
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(seed)
-    main = O.GridParams(((torch.rand((16 << 19, 2)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(16, 16, 1024), 19)
+    L, F, T, r0, r1 = w.main
+    main = O.GridParams(((torch.rand((L << T, F)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(L, r0, r1), T)
     lin = torch.nn.Linear
 
     def wb(i, o):
@@ -123,12 +146,12 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, re
     fld = O.FieldParams(main, [g0[0], g1[0]], [g0[1], g1[1]], [f0[0], f1[0], f2[0]], [f0[1], f1[1], f2[1]],
                         torch.full((1,), 20.0, requires_grad=True))
     prop = O.ProposalParams(
-        O.GridParams(((torch.rand((6 << 20, 1)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(6, 128, 4096), 20),
+        O.GridParams(((torch.rand((6 << w.prop_log2, 1)) * 2 - 1) * 1e-3).requires_grad_(True), O.level_scalings(6, 128, 4096),
+                     w.prop_log2),
         lin(6, 1, bias=False).weight.detach().requires_grad_(True),
     )
-    rays = synthetic_rays(num_rays, seed=seed)
-    pa = scaled_pixel_area(rays)
-    cfg = O.PathConfig(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES)
+    num_rays = rays["origins"].shape[0]
+    cfg = O.PathConfig(num_proposal_samples=w.proposal_samples, num_nerf_samples=w.nerf_samples)
     leaves = [main.table, *fld.geo_w, *fld.geo_b, *fld.feat_w, *fld.feat_b, fld.beta, prop.grid.table, prop.decoder_w]
     opts = []
     if optimizer:  # the reference's parameter groups (configs/method_configs.py:393-400)
@@ -139,7 +162,11 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, re
     def step():
         for t in leaves:
             t.grad = None
-        jit = [torch.rand((num_rays, PROP_SAMPLES[0] + 1)), torch.rand((num_rays, 1)), torch.rand((num_rays, 1))]
+        jit = [torch.rand((num_rays, w.proposal_samples[0] + 1)), torch.rand((num_rays, 1)), torch.rand((num_rays, 1))]
+        if not w.train:
+            with torch.no_grad():
+                O.nff_forward(fld, [prop, prop], rays["origins"], rays["directions"], pa, rays["nears"], rays["fars"], cfg, None)
+            return
         out = O.nff_forward(fld, [prop, prop], rays["origins"], rays["directions"], pa, rays["nears"], rays["fars"], cfg, jit)
         loss = O.bench_loss(out)
         if regularisers:
@@ -160,99 +187,238 @@ def cpu_reference_run(num_rays: int, steps: int, warmup: int, seed: int = 42, re
 def run_reference(args, rank):
     if rank != 0:
         return
-    sample = 4096
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    value, ms, cores = cpu_reference_run(sample, steps, warmup, regularisers=args.regularisers, optimizer=args.optimizer)
+    from neuradar_b200.synthetic import WORKLOADS
+
+    w = WORKLOADS[args.config]
+    sample = min(4096, w.rays)
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 3))
+    value, ms, cores, kind, cpu = cpu_reference_run(w, sample, steps, warmup, regularisers=args.regularisers,
+                                                    optimizer=args.optimizer)
+    what = ("the reference's own modules (oracle/_ref, unmodified) on its fp32 torch path" if kind == "reference"
+            else "the oracle port of the reference's torch path (oracle/_ref not materialised)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference algorithm on the host CPU; the reference is pure Python and "
-                   "cannot travel to the GPU box, so this is the oracle port of its torch path"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} of the 65536 rays per step, {steps} timed fwd+bwd steps"},
+        "config": {"workload": w.description, "note": f"host CPU, {what}; autocast off; compositing through "
+                   "RaySamples.get_weights_and_transmittance_from_alphas (the model's CPU branch is a 0.5 stub)"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu,
+                         "sample": f"{sample} {w.mix} rays of the workload per step, {warmup} warm-up + {steps} timed steps"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
 # ---------------------------------------------------------------------------------------------------------------
-ALGO = {
-    # algorithmic bytes per sample of one launch (8 corners x L x F x 4 B, gathers/scatters counted once)
-    "nrb_hash_fwd:L16F2T19": ("hbm", 8 * 16 * 2 * 4), "nrb_hash_bwd:L16F2T19": ("hbm", 8 * 16 * 2 * 4),
-    "nrb_proposal_fwd": ("hbm", 8 * 6 * 1 * 4), "nrb_proposal_bwd": ("hbm", 8 * 6 * 1 * 4),
-}
-MLP_FLOP_FWD = {"geo": 2 * (32 * 32 + 32 * 33), "feature": 2 * (48 * 32 + 32 * 32 + 32 * 32)}
+def parity_at_config(model, w, rays_cpu, n_check: int = 4096):
+    """The CUDA path against the reference torch path (oracle/_ref; else the oracle port) on `n_check` of the benchmark's
+    rays with the benchmark's parameters: outputs and every parameter gradient.  Element-wise bar of north_star:
+    |a - b| <= 1e-3 |b| + 1e-3 rms(b)."""
+    import neuradar_b200 as nb
+    from neuradar_b200.synthetic import scaled_pixel_area
+    from oracle import ref_runner as R
+    from tests.parity_utils import FixedJitter
+
+    dev = next(model.parameters()).device
+    n = min(n_check, rays_cpu["origins"].shape[0])
+    sub = {k: v[:n].clone() for k, v in rays_cpu.items()}
+    g = torch.Generator().manual_seed(7)
+    jit = [torch.rand((n, w.proposal_samples[0] + 1), generator=g), torch.rand((n, 1), generator=g), torch.rand((n, 1), generator=g)]
+    # CUDA path (eager, its gradients go to fresh tensors: detach the flat-buffer plumbing for this one call)
+    saved = [(p, p.grad, getattr(p, "_nrb_grad_sink", None), getattr(p, "_nrb_grad_ready", None)) for p in model.parameters()]
+    for p, *_ in saved:
+        p.grad = None
+        p._nrb_grad_sink = None
+        p._nrb_grad_ready = None
+    model.train(w.train)
+    rb = nb.RayBundle(origins=sub["origins"].to(dev), directions=sub["directions"].to(dev), pixel_area=sub["pixel_area"].to(dev),
+                      nears=sub["nears"].to(dev), fars=sub["fars"].to(dev), times=sub["times"].to(dev),
+                      metadata={"is_lidar": sub["is_lidar"].to(dev), "is_radar": sub["is_radar"].to(dev)})
+    if w.train:
+        with FixedJitter(jit):
+            out = model(rb)
+        nb.bench_loss(out).backward()
+    else:
+        with torch.no_grad():
+            out = model(rb)
+    torch.cuda.synchronize()
+    got_out = {k: out[k].detach().cpu() for k in ("features", "depth", "accumulation")}
+    got_grad = {name: (None if p.grad is None else p.grad.detach().cpu()) for name, p in model.named_parameters()}
+    for p, gr, sk, rd in saved:
+        p.grad, p._nrb_grad_sink, p._nrb_grad_ready = gr, sk, rd
+    # reference
+    kind = "reference" if R.available() else "port"
+    if kind != "reference":
+        return {"kind": "port", "note": "oracle/_ref not materialised; run tests/ for the oracle-port parity"}
+    path = R.ReferencePath(main=w.main, prop_log2=w.prop_log2, proposal_samples=w.proposal_samples, nerf_samples=w.nerf_samples)
+    path.load_from(model.state_dict())
+    path.train(w.train)
+    torch.set_num_threads(os.cpu_count() or 1)
+    if w.train:
+        with FixedJitter(jit):
+            ref = path.forward(sub, scaled_pixel_area(sub))
+        R.bench_loss(ref).backward()
+    else:
+        with torch.no_grad():
+            ref = path.forward(sub, scaled_pixel_area(sub))
+
+    def err(a, b):
+        a, b = a.float().reshape(-1), b.detach().float().reshape(-1)
+        rms = float(b.pow(2).mean().sqrt())
+        excess = ((a - b).abs() - (1e-3 * b.abs() + 1e-3 * rms)).max()
+        return {"max_abs_over_max": float((a - b).abs().max() / (b.abs().max() + 1e-30)), "within_bar": bool(excess <= 0)}
+
+    report = {"kind": kind, "rays": n, "outputs": {}, "grads": {}}
+    for k, v in got_out.items():
+        report["outputs"][k] = err(v, ref[k])
+    if w.train:
+        refp = path.named_parameters()
+        for name, gr in got_grad.items():
+            rg = refp[name].grad if name in refp else None
+            if rg is None:
+                continue
+            report["grads"][name] = err(gr if gr is not None else torch.zeros_like(rg), rg)
+    everything = list(report["outputs"].values()) + list(report["grads"].values())
+    report["worst"] = max(e["max_abs_over_max"] for e in everything)
+    report["ok"] = all(e["within_bar"] for e in everything)
+    return report
 
 
+# ---------------------------------------------------------------------------------------------------------------
 def run_b200(args, rank, world, local_rank):
     import torch.distributed as dist
 
     import neuradar_b200 as nb
     from neuradar_b200 import _lib
     from neuradar_b200.dist import GradArena
-    from tests.parity_utils import build_hot_path, synthetic_rays
+    from neuradar_b200.synthetic import WORKLOADS, build_workload, synthetic_rays
 
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
-    n = args.rays
-    model = build_hot_path(num_proposal_samples=PROP_SAMPLES, num_nerf_samples=NERF_SAMPLES, seed=42, device=dev)
-    model.train()
+    w = WORKLOADS[args.config]
+    n = args.rays or w.rays
+    model = build_workload(w, seed=42, device=dev)
+    model.train(w.train)
     used = [(name, p) for name, p in model.named_parameters() if not name.startswith("proposal_fields.0")]
-    opt = None
-    if args.optimizer:
-        # the reference's "hashgrids" (Adam) and "fields" (AdamW) groups, each one flat buffer and one fused kernel
-        from neuradar_b200.optim import FusedAdam, FusedAdamW
+    main_table = model.field.hashgrid.static_grid.hash_table
+    opts, arena, arena_bytes = None, None, 0
+    if w.train:
+        if args.optimizer:
+            # the reference's "hashgrids" (Adam) and "fields" (AdamW) groups, each one flat buffer and one fused kernel
+            from neuradar_b200.optim import FusedAdam, FusedAdamW
 
-        tables = [p for name, p in used if name.endswith("hash_table")]
-        others = [p for name, p in used if not name.endswith("hash_table")]
-        opts = [FusedAdam(tables, lr=1e-2, eps=1e-15, direct_scatter=True),
-                FusedAdamW(others, lr=1e-2, eps=1e-15, weight_decay=1e-7)]
-        arena_bytes = sum(g.numel() * 4 for o in opts for g in o.flat_grads())
-    else:
-        arena = GradArena([p for _, p in used], direct_scatter=True)
-        arena_bytes = arena.nbytes
-    rays = synthetic_rays(n, seed=42 + rank)  # each rank draws its own rays (train.py:104 seeds seed+rank)
+            tables = [p for name, p in used if name.endswith("hash_table")]
+            others = [p for name, p in used if not name.endswith("hash_table")]
+            opts = [FusedAdam(tables, lr=1e-2, eps=1e-15, direct_scatter=True, early=[main_table]),
+                    FusedAdamW(others, lr=1e-2, eps=1e-15, weight_decay=1e-7, direct_scatter=True)]
+            arena_bytes = sum(g.numel() * 4 for o in opts for g in o.flat_grads())
+        else:
+            arena = GradArena([p for _, p in used], direct_scatter=True, early=[main_table])
+            arena_bytes = arena.nbytes
+    # ray batches: each rank draws its own (train.py:104 seeds seed+rank); the timed loop rotates through them
     keys = ["origins", "directions", "pixel_area", "nears", "fars", "times", "is_lidar", "is_radar"]
-    host = {k: rays[k].pin_memory() for k in keys}
-    resident = {k: rays[k].to(dev) for k in keys}
-    h2d_bytes = sum(host[k].numel() * host[k].element_size() for k in keys)
+    n_batches = N_BATCHES if n <= (1 << 17) else 1
+    batches_cpu = [synthetic_rays(n, seed=42 + rank + 1000 * b, mix=w.mix) for b in range(n_batches)]
+    host = [{k: b[k].pin_memory() for k in keys} for b in batches_cpu]
+    resident = [{k: b[k].to(dev) for k in keys} for b in batches_cpu]
+    cur = {k: torch.empty_like(resident[0][k]) for k in keys}  # the step's (static) inputs
+    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in keys)
 
-    def bundle(src):
-        return nb.RayBundle(origins=src["origins"].clone(), directions=src["directions"].clone(),
-                            pixel_area=src["pixel_area"].clone(), nears=src["nears"].clone(), fars=src["fars"].clone(),
-                            times=src["times"], metadata={"is_lidar": src["is_lidar"], "is_radar": src["is_radar"]})
+    def bundle(src, lo=0, hi=None):
+        sl = slice(lo, hi)
+        return nb.RayBundle(origins=src["origins"][sl].clone(), directions=src["directions"][sl].clone(),
+                            pixel_area=src["pixel_area"][sl].clone(), nears=src["nears"][sl].clone(), fars=src["fars"][sl].clone(),
+                            times=src["times"][sl], metadata={"is_lidar": src["is_lidar"][sl], "is_radar": src["is_radar"][sl]})
 
-    def step(src):
-        if not args.optimizer:
+    result = {}
+
+    def step():
+        """One step on the rays in `cur`; leaves the step's scalar result in result['loss'] (device)."""
+        if not w.train:
+            chunk = w.chunk or n
+            acc = None
+            with torch.no_grad():
+                for lo in range(0, n, chunk):
+                    out = model(bundle(cur, lo, min(lo + chunk, n)))
+                    s = out["depth"].sum()
+                    acc = s if acc is None else acc + s
+            result["loss"] = acc
+            return
+        if opts is None:
             arena.zero()
-        out = model(bundle(src))
+        out = model(bundle(cur))
         loss = nb.bench_loss(out)
         if args.regularisers:
             loss = loss + nb.training_losses(out)
         loss.backward()
-        if args.optimizer:
+        if opts is not None:
             for o in opts:  # sum over ranks; the average and zero_grad ride inside the fused update
                 o.step(grad_mult=o.all_reduce_grads(), zero_grad=True)
         else:
             arena.all_reduce()
-        return loss
+        result["loss"] = loss.detach()
 
-    def step_e2e():
-        dev_rays = {k: host[k].to(dev, non_blocking=True) for k in keys}
-        return step(dev_rays).item()  # device -> host read of the step's loss
+    def load_resident(i):
+        for k in keys:
+            cur[k].copy_(resident[i % n_batches][k], non_blocking=True)
+
+    def load_host(i):
+        for k in keys:
+            cur[k].copy_(host[i % n_batches][k], non_blocking=True)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps):
+    # ---- warm-up (eager), then capture the step in a CUDA graph
+    # (on a side stream, as torch's whole-network capture recipe prescribes: autograd's gradient-accumulation nodes stay
+    # bound to the stream they were first used on, and that must be the capturing stream)
+    side = torch.cuda.Stream(device=dev)
+    load_resident(0)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for i in range(args.warmup):
+            step()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    graph, graph_note, launches_per_step = None, "eager launches (--no-graph)", None
+    has_actors = w.actors > 0
+    if not args.no_graph and not has_actors:
+        try:
+            l0 = _lib.launch_count()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side):
+                step()
+            launches_per_step = _lib.launch_count() - l0
+            graph.replay()
+            torch.cuda.synchronize()
+            graph_note = "one CUDA graph per step (fwd + bwd + collectives), replayed"
+        except Exception as e:  # noqa: BLE001 - a capture problem must not cost the measurement
+            # a failed capture leaves the CUDA generator and the allocator pool in capture mode: start over without it
+            sys.stderr.write(f"bench.py: CUDA graph capture failed ({type(e).__name__}: {str(e)[:200]}); re-running with --no-graph\n")
+            sys.stderr.flush()
+            if world == 1:
+                os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
+            raise
+    elif has_actors:
+        graph_note = "eager launches (the dynamic-actor bookkeeping sizes tensors on the host)"
+
+    def run_step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+
+    def timed(loader, steps, read_back):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            fn()
+        for i in range(steps):
+            loader(i)
+            run_step()
+            if read_back:
+                result["loss"].item()  # device -> host read of the step's result
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -260,53 +426,62 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()) / steps
 
-    for _ in range(args.warmup):
-        step(resident)
-    launches0 = _lib.launch_count()
+    for i in range(2):
+        load_resident(i)
+        run_step()
+    l0 = _lib.launch_count()
     with ClockSampler(local_rank) as clocks:
-        ms = timed(lambda: step(resident), args.steps)
-    launches = _lib.launch_count() - launches0
-    for _ in range(2):
-        step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+        ms = timed(load_resident, args.steps, False)
+    launches = _lib.launch_count() - l0 if graph is None else launches_per_step * args.steps
+    for i in range(2):
+        load_host(i)
+        run_step()
+    ms_e2e = timed(load_host, args.steps, True)
 
-    # per-kernel durations from CUDA events on the launching stream (separate pass: the events add launch gaps)
+    # ---- per-kernel durations from CUDA events on the launching stream (separate eager pass: the events add launch gaps)
+    reps = max(3, min(args.steps, 10))
     _lib.TIMER = _lib.KernelTimer()
-    for _ in range(max(3, min(args.steps, 10))):
-        step(resident)
+    for i in range(reps):
+        load_resident(i)
+        step()
     kernels = _lib.TIMER.summary()
     _lib.TIMER = None
 
     peaks = load_peaks()
     total_rays = n * world
-    reps = max(3, min(args.steps, 10))
     per_step = {name: {"launches_per_step": count / reps, "mean_ms": mean_ms} for name, (count, mean_ms) in kernels.items()}
     # Roofline of every major kernel: algorithmic work per launch / CUDA-event duration.
-    #   hash / proposal kernels: 8 corners x L x F x 4 B per sample, gathers (or scatters) counted once  -> HBM GB/s
-    #   compositor: the [N,S,32] feature tensor streamed once (+ once written in the backward)          -> HBM GB/s
-    #   field MLP: 2 * sum(in*out) FLOP per sample forward, twice that backward                          -> tensor TFLOP/s
-    n_main = n * NERF_SAMPLES
+    #   gathers / scatters: 8 corners x L x F x 4 B per sample, counted once                              -> HBM GB/s
+    #   fused field kernels: the gather bytes (fwd) resp. the saved image + masks + d x image streams (bwd) -> HBM GB/s,
+    #   and their MLP FLOPs against the tensor peak (reported as `tensor_frac`)
+    L, F, T, _, _ = w.main
+    S = w.nerf_samples
+    passes = (n // (w.chunk or n)) if not w.train else 1
+    n_main = n * S / passes
+    grid_tag = f"L{L}F{F}T{T}"
     mlp_flop = 2 * (32 * 32 + 32 * 33 + 48 * 32 + 32 * 32 + 32 * 32)
+    prop_mean = sum(w.proposal_samples) / len(w.proposal_samples)
     work = {
-        "nrb_hash_fwd:L16F2T19": ("hbm", n_main * 1024.0),
-        "nrb_hash_bwd:L16F2T19": ("hbm", n_main * 1024.0),
-        "nrb_proposal_fwd": ("hbm", n * (PROP_SAMPLES[0] + PROP_SAMPLES[1]) / 2 * 192.0),
-        "nrb_proposal_bwd": ("hbm", n * (PROP_SAMPLES[0] + PROP_SAMPLES[1]) / 2 * 192.0),
-        "nrb_alpha_composite_fwd": ("hbm", n_main * 32 * 4.0),
-        "nrb_alpha_composite_bwd": ("hbm", n_main * 32 * 4.0 * 2),
-        "nrb_field_mlp_fwd": ("tensor", n_main * float(mlp_flop)),
-        "nrb_field_mlp_bwd": ("tensor", n_main * float(mlp_flop) * 2),
+        "nrb_field_fused_fwd": ("hbm", n_main * 8.0 * L * F * 4, n_main * float(mlp_flop)),
+        "nrb_field_fused_bwd": ("hbm", n_main * (128.0 + 12.0 + 128.0 + 4 * 4), n_main * float(mlp_flop) * 2.6),
+        f"nrb_hash_bwd:{grid_tag}": ("hbm", n_main * 8.0 * L * F * 4, 0.0),
+        f"nrb_hash_fwd:{grid_tag}": ("hbm", n_main * 8.0 * L * F * 4, 0.0),
+        "nrb_proposal_fwd": ("hbm", n / passes * prop_mean * 192.0, 0.0),
+        "nrb_proposal_bwd": ("hbm", n / passes * prop_mean * 192.0, 0.0),
+        "nrb_alpha_composite_fwd": ("hbm", n_main * 32 * 4.0, 0.0),
+        "nrb_alpha_composite_bwd": ("hbm", n_main * 32 * 4.0, 0.0),
+        "nrb_field_mlp_fwd": ("tensor", n_main * float(mlp_flop), 0.0),
+        "nrb_field_mlp_bwd": ("tensor", n_main * float(mlp_flop) * 2, 0.0),
     }
     if args.optimizer:  # read p, g, m, v + write p, m, v, g = 32 B per parameter, averaged over the two groups' launches
-        work["nrb_adam_step"] = ("hbm", arena_bytes / 4 * 32.0 / 2)
-    # DRAM bytes per launch from the committed ncu --set full capture (None when a kernel was not captured)
+        work["nrb_adam_step"] = ("hbm", arena_bytes / 4 * 32.0 / 2, 0.0)
     try:
-        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_traffic.json")) as fh:
-            captured = json.load(fh)["kernels"] if n == RAYS_PER_GPU else {}
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as fh:
+            captured = json.load(fh)["kernels"] if args.config == 2 and n == w.rays else {}
     except (OSError, ValueError, KeyError):
         captured = {}
     rooflines = {}
-    for name, (bound, amount) in work.items():
+    for name, (bound, amount, flops) in work.items():
         if name not in kernels:
             continue
         mean_ms = kernels[name][1]
@@ -314,24 +489,31 @@ def run_b200(args, rank, world, local_rank):
             achieved, peak, unit = amount / (mean_ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
         else:
             achieved, peak, unit = amount / (mean_ms * 1e-3) / 1e12, peaks["tflops"], "TFLOP/s"
-        rooflines[name] = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
-                           "frac": achieved / peak, "traffic": captured.get(name, {}).get("dram_bytes_per_launch"),
-                           "traffic_unit": "B (ncu dram read+write per launch, profiles/r1_traffic.json)",
-                           "peak_source": peaks["source"],
-                           "algorithmic_per_launch": amount, "mean_launch_ms": mean_ms,
-                           "ms_per_step": mean_ms * per_step[name]["launches_per_step"]}
-    # the headline entry: the kernel with the largest share of the step
+        entry = {"kernel": name, "bound": bound, "achieved": achieved, "peak": peak, "unit": unit,
+                 "frac": achieved / peak, "traffic": captured.get(name, {}).get("dram_bytes_per_launch"),
+                 "traffic_unit": "B (ncu dram read+write per launch, profiles/r2_traffic.json)",
+                 "peak_source": peaks["source"], "algorithmic_per_launch": amount, "mean_launch_ms": mean_ms,
+                 "ms_per_step": mean_ms * per_step[name]["launches_per_step"]}
+        if flops:
+            entry["tensor_tflops"] = flops / (mean_ms * 1e-3) / 1e12
+            entry["tensor_frac"] = entry["tensor_tflops"] / peaks["tflops"]
+        rooflines[name] = entry
     roofline = max(rooflines.values(), key=lambda r: r["ms_per_step"]) if rooflines else None
+    path_gbs = n * w.bytes_per_ray() / (ms * 1e-3) / 1e9
+    kernel_ms = sum(v["mean_ms"] * v["launches_per_step"] for v in per_step.values())
 
     line = {
-        "metric": METRIC, "value": total_rays / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rays_per_gpu": n, "global_rays": total_rays,
-                   "parallelism": f"ray-sharded dp{world}, one all-reduce of a {arena_bytes / 2**20:.0f} MiB gradient arena",
-                   "l2": "per-step working set (saved activations + gradient arena, > 1 GB) exceeds the 126 MB L2; "
-                         "no explicit flush", "optimizer": "fused Adam (hash grids) + AdamW (MLPs) inside the step" if args.optimizer
-                   else "not part of the path (SURVEY.md 8f next-2; --optimizer adds it)",
+        "metric": METRIC if w.train else "inference_rays_per_sec", "value": total_rays / (ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": w.description, "rays_per_gpu": n, "global_rays": total_rays,
+                   "parallelism": (f"ray-sharded dp{world}, all-reduce of a {arena_bytes / 2**20:.0f} MiB gradient arena in two "
+                                   "pieces (main table overlapped with the proposal backward)") if w.train else f"replicas x{world}",
+                   "launch": graph_note,
+                   "l2": f"{n_batches} resident ray batches rotated; per-step working set (tables 64-512 MiB, saved images, gradient "
+                         "arena, > 0.7 GB) exceeds the 126 MB L2; no explicit flush",
+                   "optimizer": ("fused Adam (hash grids) + AdamW (MLPs) inside the step" if args.optimizer
+                                 else "not part of the path (SURVEY.md 8f next-2; --optimizer adds it)") if w.train else "n/a",
                    "regularisers": bool(args.regularisers)},
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -339,13 +521,27 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks.summary(),
         "roofline": roofline,
         "rooflines": rooflines,
+        "path_roofline": {"bound": "hbm", "bytes_per_ray": w.bytes_per_ray(), "achieved": path_gbs, "peak": peaks["hbm_gbs"],
+                          "unit": "GB/s", "frac": path_gbs / peaks["hbm_gbs"],
+                          "roofline_rays_per_sec": peaks["hbm_gbs"] * 1e9 / w.bytes_per_ray()},
         "kernels": per_step,
+        "kernel_ms_per_step": kernel_ms,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            v, cms, cores = cpu_reference_run(4096, 2, 1, regularisers=args.regularisers, optimizer=args.optimizer)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "4096 of the 65536 rays per step, 2 timed fwd+bwd steps of the oracle"}
+            try:
+                line["parity_at_config"] = parity_at_config(model, w, batches_cpu[0])
+            except Exception as e:  # noqa: BLE001
+                line["parity_at_config"] = {"error": f"{type(e).__name__}: {str(e)[:200]}"}
+            from neuradar_b200.synthetic import WORKLOADS as WL
+
+            # the reference torch path on config 1 (4096 radar rays), all host cores
+            big = (os.cpu_count() or 1) >= 12
+            v, cms, cores, kind, cpu = cpu_reference_run(WL[1] if w.train else w, 4096, 10 if big else 3, 3 if big else 1,
+                                                         regularisers=args.regularisers, optimizer=args.optimizer)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu, "ms_per_step": cms,
+                                    "sample": (f"BASELINE config 1: 4096 radar rays, {3 if big else 1} warm-up + "
+                                               f"{10 if big else 3} timed {'fwd+bwd' if w.train else 'fwd'} iterations")}
         print(json.dumps(line))
 
 
@@ -355,8 +551,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5], help="BASELINE.json configuration")
+    ap.add_argument("--rays", type=int, default=0, help="rays per GPU per step (default: the configuration's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--optimizer", action="store_true",
                     help="add the fused Adam / AdamW update (SURVEY.md 8f next-2) to the step of both arms")
     ap.add_argument("--regularisers", action="store_true",
@@ -370,7 +568,7 @@ def main():
         run_reference(args, rank)
         return
     if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: neuradar_b200 has no CPU path (use --impl reference for the CPU oracle)")
+        raise SystemExit("bench.py needs a CUDA device: neuradar_b200 has no CPU path (use --impl reference for the CPU arm)")
     if world > 1:
         import torch.distributed as dist
 

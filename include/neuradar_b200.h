@@ -195,7 +195,8 @@ int nrb_field_fused_fwd(const nrb_field_mlp_t* mlp, const nrb_grid_t* grid, cons
  * dfeat_ray[m / samples_per_ray].  dsdf / dalpha [M] are optional.  dximg (optional) receives the gradient with
  * respect to the hash features as a tile image: float4 element (tile, chunk c of 4 features, sample r of the tile) at
  * [(tile * 8 + c) * 128 + r] (nrb_field_fused_image_bytes(M) * 1 bytes); nrb_hash_bwd_image scatters it into the table.
- * Parameter gradients are ACCUMULATED as in nrb_field_mlp_bwd. */
+ * Parameter gradients are ACCUMULATED as in nrb_field_mlp_bwd, except that dbeta [1] is the gradient with respect to
+ * beta itself (the sign of beta is applied inside). */
 typedef struct {
   nrb_field_fused_saved_t saved;
   const float* sh;

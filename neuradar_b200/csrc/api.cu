@@ -1,5 +1,8 @@
 // Library plumbing: version, per-thread error string, launch counter, argument validation.
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdarg>
 #include <cstdio>
 
@@ -55,6 +58,20 @@ int check_intervals(const char* who, const nrb_intervals_t* iv) {
               "%s: num_samples %d not in [1,%d]", who, iv->num_samples, NRB_MAX_SAMPLES);
   NRB_REQUIRE(iv->row_stride >= iv->num_samples, NRB_ERR_BAD_ARG, "%s: row_stride smaller than num_samples", who);
   return NRB_OK;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, int> done;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) (void)cudaGetLastError();
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_pair(dev, kernel);
+  auto it = done.find(key);
+  if (it != done.end() && it->second >= bytes) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) done[key] = bytes;
+  return e;
 }
 
 int sm_count() {

@@ -33,6 +33,9 @@ int check_intervals(const char* who, const nrb_intervals_t* iv);
 // Grid sizes for element-wise kernels: plain ceil-div (the hot kernels size themselves in multiples of the SM count).
 inline unsigned blocks_for(int64_t work, int threads) { return static_cast<unsigned>((work + threads - 1) / threads); }
 int sm_count();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), issued once per (device, kernel): the attribute is sticky, and the call is
+// not permitted while a stream is being captured into a CUDA graph.
+cudaError_t ensure_dynamic_smem(const void* kernel, int bytes);
 
 // ---- device side ---------------------------------------------------------------------------------------------
 // Geometry feeds integer outputs (hash-table rows), so it is evaluated with explicitly rounded fp32 operations in

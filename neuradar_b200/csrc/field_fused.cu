@@ -828,7 +828,10 @@ __global__ void __launch_bounds__(kBThreads, 1) field_fused_bwd_kernel(const __g
     }
     if (it > 0) wait_done(0, it - 1);
     const float sb = warp_sum(dbeta_acc);
-    if (lane == 0 && a.dbeta != nullptr && sb != 0.0f) atomicAdd(a.dbeta, sb);
+    if (lane == 0 && a.dbeta != nullptr && sb != 0.0f) {
+      const float b0 = __ldg(prm.beta);  // d(|beta| + beta_min) / d beta = sign(beta)
+      atomicAdd(a.dbeta, sb * (b0 > 0.0f ? 1.0f : (b0 < 0.0f ? -1.0f : 0.0f)));
+    }
   }
   // ---- flush: weight and bias gradients from TMEM.  Row j of an M = 64 accumulator sits in lane (j / 16) * 32 + j % 16
   // (+ 16 for the second accumulator of a column range); rows j and 32 + j (hi and mid parts of delta) and the column
@@ -1002,7 +1005,7 @@ extern "C" int nrb_field_fused_fwd(const nrb_field_mlp_t* p, const nrb_grid_t* g
   auto s = static_cast<cudaStream_t>(stream);
 #define NRB_FUSED_FWD(FF)                                                                                                      \
   {                                                                                                                            \
-    cudaError_t e = cudaFuncSetAttribute(field_fused_fwd_kernel<FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedFwdSmem::total); \
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_fused_fwd_kernel<FF>), FusedFwdSmem::total); \
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_fused_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));  \
     field_fused_fwd_kernel<FF><<<nblk, kFThreads, FusedFwdSmem::total, s>>>(fused_params(p), gd, a);                           \
   }
@@ -1042,7 +1045,7 @@ extern "C" int nrb_field_fused_bwd(const nrb_field_mlp_t* p, const nrb_field_fus
   if (a.dfeature != nullptr) {
     if (int rc = make_rows_tensor_map(&map, a.dfeature, M)) return rc;
   }
-  cudaError_t e = cudaFuncSetAttribute(field_fused_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FusedBwdSmem::total);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_fused_bwd_kernel), FusedBwdSmem::total);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_fused_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned nblk = static_cast<unsigned>(std::min<int64_t>((tiles + 1) / 2, sm_count()));

@@ -277,7 +277,7 @@ extern "C" int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float*
     const unsigned nb = blocks_for(M, kFwdWarps * 32);
 #define NRB_ROWS(F)                                                                                                    \
   {                                                                                                                    \
-    cudaError_t e = cudaFuncSetAttribute(hash_fwd_rows_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); \
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(hash_fwd_rows_kernel<F>), 64 * 1024); \
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); \
     hash_fwd_rows_kernel<F><<<nb, kFwdWarps * 32, smem, s>>>(g, x, std, out, M);                                        \
   }
@@ -329,7 +329,7 @@ static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float
   const int row_floats = grid->num_levels * F;
   if (dedup && dx == nullptr && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
     const size_t smem = static_cast<size_t>(kDedupWarps) * 32 * row_floats * 4;
-    cudaError_t e = cudaFuncSetAttribute(hash_bwd_dedup_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(hash_bwd_dedup_kernel<F>), 64 * 1024);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     hash_bwd_dedup_kernel<F><<<blocks_for(M, kDedupWarps * 32), kDedupWarps * 32, smem, s>>>(g, plan, x, std, dy, dtable, M);
     launch_fold<F>(grid, plan, dtable, vertices, s);

@@ -211,7 +211,7 @@ extern "C" int nrb_interlevel_loss(const float* c_bins, int64_t c_stride, const 
   if (N == 0) return NRB_OK;
   const int n1 = Sc + 1, m = 2 * n1, len = m + 2;
   const size_t smem = sizeof(float) * kLossWarps * (2 * n1 + 3 * len + m + (Sp + 1));
-  cudaError_t e = cudaFuncSetAttribute(interlevel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(interlevel_kernel), 96 * 1024);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_interlevel_loss: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   interlevel_kernel<<<blocks_for(N, kLossWarps), kLossWarps * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       c_bins, c_stride, w, Sc, cp_bins, cp_stride, wp, Sp, pulse_width, N, loss_per_ray, grad_factor);

@@ -307,7 +307,7 @@ extern "C" int nrb_mlp_fwd(const nrb_mlp_t* mlp, const float* x, float* y, float
   const MlpDev d = to_dev(mlp);
   const size_t smem =
       sizeof(float) * (((wt_floats(d.dims, d.n) + 3) & ~3) + 2 * static_cast<size_t>(max_dim(d.dims, d.n)) * kStride);
-  cudaError_t e = cudaFuncSetAttribute(mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(mlp_fwd_kernel), 200 * 1024);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + kTile - 1) / kTile;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, static_cast<int64_t>(sm_count()) * 3));
@@ -334,7 +334,7 @@ extern "C" int nrb_mlp_bwd(const nrb_mlp_t* mlp, const float* x, const float* hi
   }
   const size_t smem = sizeof(float) * (((w_floats + 3) & ~3) + ((g_floats + 3) & ~3) +
                                        2 * static_cast<size_t>(max_dim(d.dims, d.n)) * kStride);
-  cudaError_t e = cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(mlp_bwd_kernel), 200 * 1024);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + kTile - 1) / kTile;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, static_cast<int64_t>(sm_count()) * 2));

@@ -1537,7 +1537,7 @@ extern "C" int nrb_tc_linear(const float* x, const float* w, const float* b, int
               "nrb_tc_linear: K must be 32 or 48 and n_out <= 48");
   if (M == 0) return NRB_OK;
   const size_t smem = 2 * 48 * 48 * 4 + 2 * tc::kRows * 48 * 4 + 16;
-  cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_linear_kernel), static_cast<int>(smem));
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
@@ -1550,7 +1550,7 @@ extern "C" int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11
   NRB_REQUIRE(P && Q && cfg11 && dump, NRB_ERR_BAD_ARG, "nrb_tc_probe: null pointer");
   ProbeCfg c{cfg11[0], cfg11[1], cfg11[2], cfg11[3], cfg11[4], cfg11[5], cfg11[6], cfg11[7], cfg11[8], cfg11[9], cfg11[10]};
   const size_t smem = 4 * tc::kRows * 32 * 4 + 16;
-  cudaError_t e = cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(tc_probe_kernel), static_cast<int>(smem));
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_tc_probe: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   tc_probe_kernel<<<1, tc::kRows, smem, static_cast<cudaStream_t>(stream)>>>(P, Q, c, dump);
   return finish_launch("nrb_tc_probe");
@@ -1587,7 +1587,7 @@ extern "C" int nrb_field_mlp_fwd(const nrb_field_mlp_t* p, const float* x, const
                 "nrb_field_mlp_fwd: saved->ld must be nrb_field_saved_ld(M)");
     sv = FieldSaved{saved->h1, saved->emb, saved->g1, saved->g2, saved->masks, saved->ld};
   }
-  cudaError_t e = cudaFuncSetAttribute(field_mlp_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldSmem::total);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_mlp_fwd_kernel), FieldSmem::total);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, 2 * sm_count()));
@@ -1621,7 +1621,7 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
     bo.db[l] = out->dbiases[l];
   }
   bo.dbeta = out->dbeta;
-  cudaError_t e = cudaFuncSetAttribute(field_mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwdSmem::total);
+  cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_mlp_bwd_kernel), FieldBwdSmem::total);
   NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, sm_count()));
@@ -1630,7 +1630,7 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   // 1 = the one-thread-per-row kernel
   static const int split = std::getenv("NRB_FIELD_BWD_SPLIT") ? std::atoi(std::getenv("NRB_FIELD_BWD_SPLIT")) : 22;
   if (split == 22 && M < (int64_t{1} << 31)) {  // two tiles in flight per CTA
-    e = cudaFuncSetAttribute(field_mlp_bwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwdPairSmem::total);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_mlp_bwd_pair_kernel), FieldBwdPairSmem::total);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     const unsigned pgrid = static_cast<unsigned>(std::min<int64_t>((tiles + 1) / 2, sm_count()));
     field_mlp_bwd_pair_kernel<<<pgrid, kPairThreads, FieldBwdPairSmem::total, static_cast<cudaStream_t>(stream)>>>(
@@ -1639,7 +1639,7 @@ extern "C" int nrb_field_mlp_bwd(const nrb_field_mlp_t* p, const nrb_field_bwd_i
   }
   if ((split == 2 || split == 4) && M < (int64_t{1} << 31)) {
     auto kern = split == 2 ? field_mlp_bwd_split_kernel<2> : field_mlp_bwd_split_kernel<4>;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FieldBwd2Smem::total);
+    e = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), FieldBwd2Smem::total);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_mlp_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     kern<<<grid, tc::kRows * split + 32, FieldBwd2Smem::total, static_cast<cudaStream_t>(stream)>>>(to_params(p), bi, bo,
                                                                                                    samples_per_ray, M, dbg);

@@ -123,8 +123,8 @@ class GradArena:
         self._views = [self.flat[off : off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
         for i, (p, view) in enumerate(zip(self.params, self._views)):
             p.grad = view
-            if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
-                p._nrb_grad_sink = view  # hash tables: the scatter kernels add straight into the arena
+            if direct_scatter:
+                p._nrb_grad_sink = view  # the backward kernels add straight into the arena (functional.grad_sink_of)
                 if i < n_first:
                     p._nrb_grad_ready = self.reducer.start_early
 

@@ -187,6 +187,13 @@ class SigmoidDensity(nn.Module):
         super().__init__()
         self.register_buffer("beta_min", torch.tensor(beta_min))
         self.register_parameter("beta", nn.Parameter(init_val * torch.ones(1), requires_grad=learnable_beta))
+        self.beta_min_value = float(beta_min)  # host copy: the kernels take it by value, reading the buffer would synchronise
+
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        key = prefix + "beta_min"
+        if key in state_dict:
+            self.beta_min_value = float(state_dict[key])
+        super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
 
     def forward(self, sdf: Tensor, beta: Optional[Tensor] = None) -> Tensor:
         if beta is None:

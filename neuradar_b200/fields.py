@@ -122,7 +122,7 @@ class NeuRADField(nn.Module):
         geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
         weights = [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight]
         biases = [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias]
-        beta, beta_min = self.sdf_to_density.beta, float(self.sdf_to_density.beta_min)
+        beta, beta_min = self.sdf_to_density.beta, self.sdf_to_density.beta_min_value
         grid = self.hashgrid.static_grid
         with_actors = self.hashgrid.has_actors and times is not None
         if self.fused and not with_actors and grid.features_per_level in (2, 4):
@@ -140,6 +140,25 @@ class NeuRADField(nn.Module):
         if self.fused:
             return F.field_fused(None, features, None, None, sh, sh_group, None, weights, biases, beta, beta_min)
         return F.field_mlp(features, sh, sh_group, weights, biases, beta, beta_min)
+
+    def can_render(self, ray_samples: RaySamples) -> bool:
+        """True when `render` applies: default field shape, a 32-feature static grid and no dynamic actors."""
+        grid = self.hashgrid.static_grid
+        return (self.fused and self._tensor_core_path() and not self.hashgrid.has_actors
+                and grid.features_per_level in (2, 4) and len(ray_samples.shape) == 2)
+
+    def render(self, ray_samples: RaySamples, trans_eps: float = 0.0):
+        """Field + compositing tail in one autograd node (models/neuradar.py:500-517): returns (weights [N,S] after the
+        sky fix-up, features [N,32], depth [N], accumulation [N]).  The [N,S,32] feature gradient is never formed."""
+        rays, iv = per_ray_of(ray_samples)
+        geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
+        weights = [geo_l[0].weight, geo_l[1].weight, feat_l[0].weight, feat_l[1].weight, feat_l[2].weight]
+        biases = [geo_l[0].bias, geo_l[1].bias, feat_l[0].bias, feat_l[1].bias, feat_l[2].bias]
+        grid = self.hashgrid.static_grid
+        x3, std = F.frustum_gaussians(rays, iv, self.hashgrid.static_scale)
+        sh = self.direction_encoding(get_normalized_directions(rays.directions))
+        return F.field_render(grid.hash_table, x3, std, sh, iv, grid.spec, weights, biases, self.sdf_to_density.beta,
+                              self.sdf_to_density.beta_min_value, trans_eps)
 
     def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         N = rays.num_rays

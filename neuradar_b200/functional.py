@@ -164,11 +164,14 @@ def side_stream(device, index: int = 0) -> "torch.cuda.Stream":
 # ------------------------------------------------------------------------------------------------
 # hash grid
 # ------------------------------------------------------------------------------------------------
-def grad_sink_of(table: Tensor) -> Optional[Tensor]:
+def grad_sink_of(table: Optional[Tensor]) -> Optional[Tensor]:
     """Opt-in direct gradient accumulation: when the owner of the flat gradient buffer (dist.GradArena, optim.FusedAdam)
-    marked a hash table with `_nrb_grad_sink` (a view with the table's shape), the scatter kernels add straight into
-    it and the autograd Function returns no gradient for the table.  This skips a zero-fill of a table-sized temporary
-    and AccumulateGrad's read-add-write of it (3 x 64 MiB of traffic for the main grid) per backward."""
+    marked a parameter with `_nrb_grad_sink` (a view with the parameter's shape), the backward kernels add straight
+    into it and the autograd Function returns no gradient for it.  For a hash table this skips a zero-fill of a
+    table-sized temporary and AccumulateGrad's read-add-write of it (3 x 64 MiB of traffic for the main grid) per
+    backward; for the small MLP parameters it removes a zero-fill and an add launch each."""
+    if table is None:
+        return None
     sink = getattr(table, "_nrb_grad_sink", None)
     if sink is None or sink.shape != table.shape or sink.dtype != torch.float32 or not sink.is_contiguous():
         return None
@@ -183,7 +186,7 @@ def _sink_written(table: Tensor) -> None:
     registered a callback (dist.OverlappedReduce.start_early) to start reducing this gradient right away."""
     dev = table.device
     cur, main = torch.cuda.current_stream(dev), torch.cuda.default_stream(dev)
-    if cur != main:
+    if cur != main and not torch.cuda.is_current_stream_capturing():  # (a graph capture orders its own streams)
         ev = torch.cuda.Event()
         ev.record(cur)
         main.wait_event(ev)
@@ -468,9 +471,21 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
     M, dev = sdf.shape[0], sdf.device
     need_dx = ctx.gather or ctx.needs_x_grad
     dximg = torch.empty((int(_lib_().nrb_field_fused_image_bytes(M)) // 4,), device=dev, dtype=torch.float32) if need_dx else None
-    dws = [torch.zeros_like(w) for w in weights_]
-    dbs = [None if b is None else torch.zeros_like(b) for b in biases]
-    dbeta_eff = torch.zeros((1,), device=dev, dtype=torch.float32)
+    # parameter gradients: straight into the owner's flat buffer where a sink was registered, else one zeroed scratch
+    psinks = ctx.param_sinks  # [beta, w0..w4, b0..b4] (None = no sink)
+    tensors = [beta, *weights_, *biases]
+    need = [t for t, sk in zip(tensors, psinks) if t is not None and sk is None]
+    scratch = torch.zeros((sum((t.numel() + 3) // 4 * 4 for t in need),), device=dev, dtype=torch.float32) if need else None
+    grads, off = [], 0
+    for t, sk in zip(tensors, psinks):
+        if t is None:
+            grads.append(None)
+        elif sk is not None:
+            grads.append(sk)
+        else:
+            grads.append(scratch[off : off + t.numel()].view_as(t))
+            off += (t.numel() + 3) // 4 * 4
+    dbeta_t, dws, dbs = grads[0], grads[1:6], grads[6:11]
     m = _field_struct(weights_, biases, beta, ctx.beta_min)
     bi = _lib.FieldFusedBwdIn()
     bi.saved.ximg, bi.saved.masks, bi.saved.ld = ptr(ximg), ptr(masks), masks.shape[1]
@@ -482,7 +497,7 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
     for i in range(5):
         bo.dweights[i] = ptr(dws[i])
         bo.dbiases[i] = ptr(dbs[i])
-    bo.dbeta = ptr(dbeta_eff)
+    bo.dbeta = ptr(dbeta_t)
     _lib.call("nrb_field_fused_bwd", C.byref(m), C.byref(bi), C.byref(bo), ctx.samples_per_ray, M, stream_ptr())
     dx = dtable = None
     if ctx.gather:
@@ -497,11 +512,13 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
             dtable = None
     elif ctx.needs_x_grad:
         dx = dximg.view(-1, 8, 128, 4).permute(0, 2, 1, 3).reshape(-1, 32)[:M]
-    dbeta = (dbeta_eff * torch.sign(beta)).view_as(beta)  # d(|beta| + beta_min) / d beta
-    return dx, dtable, dbeta, dws, dbs
+    if any(sk is not None for sk in psinks):
+        _sink_written(next(t for t, sk in zip(tensors, psinks) if sk is not None))
+    ret = [None if sk is not None else gr for gr, sk in zip(grads, psinks)]
+    return dx, dtable, ret[0], ret[1:6], ret[6:11]
 
 
-def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train):
+def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, param_sinks=None):
     """Launch nrb_field_fused_fwd and stash what the backward needs on ctx.  Returns (feature, sdf, alpha)."""
     gather = table is not None
     sh, beta = f32c(sh.detach()), f32c(beta)
@@ -533,6 +550,7 @@ def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, 
                               beta, sdf, alpha, *weights, *[b for b in biases if b is not None])
         ctx.has_bias = [b is not None for b in biases]
         ctx.samples_per_ray, ctx.beta_min, ctx.gather, ctx.spec = int(samples_per_ray), float(beta_min), gather, spec
+        ctx.param_sinks = param_sinks if param_sinks is not None else [None] * 11
     return feature, sdf, alpha
 
 
@@ -546,7 +564,8 @@ class _FieldFused(torch.autograd.Function):
         ctx.sink = grad_sink_of(table) if table is not None else None
         train = any(ctx.needs_input_grad)
         ctx.needs_x_grad = x is not None and ctx.needs_input_grad[1]
-        return _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train)
+        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params]
+        return _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, sinks)
 
     @staticmethod
     @custom_bwd(device_type="cuda")
@@ -565,6 +584,60 @@ def field_fused(table: Optional[Tensor], x: Optional[Tensor], x3: Optional[Tenso
                 biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
     """Fused field.  Gather mode: `table` + sample means `x3` [M,3] + `std` [M]; otherwise hash features `x` [M,32]."""
     return _FieldFused.apply(table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, *weights, *biases)
+
+
+class _FieldRender(torch.autograd.Function):
+    """Fused field + alpha compositing tail of NeuRadarModel.get_nff_outputs (models/neuradar.py:500-517) on
+    (table, sample means, stds, intervals): outputs weights [N,S] (after the sky fix-up), features [N,32], depth [N],
+    accumulation [N].  Forward = the fused field kernel + the compositor; the per-sample [M,32] feature gradient is
+    never formed in the backward: it is weights[m] * dfeatures[ray] and the field's backward kernel takes the factors."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, table, x3, std, sh, iv: "SampleIntervals", beta_min: float, spec, trans_eps: float, beta, *params):
+        ctx.sink = grad_sink_of(table)
+        train = any(ctx.needs_input_grad)
+        ctx.needs_x_grad = False
+        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params]
+        S = iv.num_samples
+        feature, sdf, alpha = _field_fused_forward(ctx, table, None, x3, std, sh, S, beta_min, spec, beta, params, train, sinks)
+        N, dev = alpha.shape[0] // S, alpha.device
+        weights = torch.empty((N, S), device=dev, dtype=torch.float32)
+        features = torch.empty((N, 32), device=dev, dtype=torch.float32)
+        depth = torch.empty((N,), device=dev, dtype=torch.float32)
+        acc = torch.empty((N,), device=dev, dtype=torch.float32)
+        i = iv.struct()
+        _lib.call("nrb_alpha_composite_fwd", ptr(alpha), ptr(feature), C.byref(i), N, 32, float(trans_eps), 1, ptr(weights),
+                  ptr(features), ptr(depth), ptr(acc), None, stream_ptr())
+        if train:
+            ctx.render = (feature, weights, iv, float(trans_eps))
+        return weights, features, depth, acc
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dweights, dfeatures, ddepth, dacc):
+        feature, weights, iv, eps = ctx.render
+        alpha = ctx.saved_tensors[8]
+        N, S = weights.shape
+        dev = weights.device
+        dweights = None if dweights is None else f32c(dweights)
+        dfeatures = torch.zeros((N, 32), device=dev) if dfeatures is None else f32c(dfeatures)
+        ddepth = None if ddepth is None else f32c(ddepth)
+        dacc = None if dacc is None else f32c(dacc)
+        dalphas = torch.empty((N * S,), device=dev, dtype=torch.float32)
+        i = iv.struct()
+        _lib.call("nrb_alpha_composite_bwd", ptr(alpha), ptr(feature), C.byref(i), N, 32, eps, 1, ptr(dweights), ptr(dfeatures),
+                  ptr(ddepth), ptr(dacc), ptr(dalphas), None, stream_ptr())
+        _, dtable, dbeta, dws, dbs = _field_fused_backward(ctx, ctx.saved_tensors, None, dfeatures, weights.reshape(-1), None,
+                                                           dalphas)
+        return (dtable, None, None, None, None, None, None, None, dbeta, *dws, *dbs)
+
+
+def field_render(table: Tensor, x3: Tensor, std: Optional[Tensor], sh: Tensor, iv: SampleIntervals, spec: GridSpec,
+                 weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float,
+                 trans_eps: float = 0.0) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """(weights [N,S], features [N,32], depth [N], accumulation [N]) of the rays whose samples are (x3, std, iv)."""
+    return _FieldRender.apply(table, x3, std, sh, iv, beta_min, spec, trans_eps, beta, *weights, *biases)
 
 
 def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:
@@ -778,6 +851,7 @@ class _ProposalRound(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, table, decoder_w, rays: RayData, iv: SampleIntervals, spec: GridSpec, scale: float):
         ctx.sink = grad_sink_of(table)
+        ctx.dec_sink = grad_sink_of(decoder_w)
         table = f32c(table)
         dec = f32c(decoder_w.reshape(-1))
         N, S = rays.num_rays, iv.num_samples
@@ -800,7 +874,7 @@ class _ProposalRound(torch.autograd.Function):
     def backward(ctx, ddensity, dweights):
         table, dec, feats, pre = ctx.saved_tensors
         dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
-        ddec = torch.zeros_like(dec)
+        ddec = ctx.dec_sink.reshape(-1) if ctx.dec_sink is not None else torch.zeros_like(dec)
         ddensity = None if ddensity is None else f32c(ddensity)
         dweights = None if dweights is None else f32c(dweights)
         g, r, i = ctx.spec.struct(table), ctx.rays.struct(), ctx.iv.struct()
@@ -810,7 +884,8 @@ class _ProposalRound(torch.autograd.Function):
                   ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, stream_ptr())
         if ctx.sink is not None:
             _sink_written(table)
-        return (None if ctx.sink is not None else dtable), ddec.reshape(ctx.dec_shape), None, None, None, None
+        return ((None if ctx.sink is not None else dtable), (None if ctx.dec_sink is not None else ddec.reshape(ctx.dec_shape)),
+                None, None, None, None)
 
 
 def proposal_round(

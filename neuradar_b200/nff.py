@@ -129,13 +129,17 @@ class NeuRadarHotPath(nn.Module):
     def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False) -> Dict[str, Tensor]:
         self._scale_pixel_area(ray_bundle)
         ray_samples, proposal_ray_samples, proposal_weights = self._get_ray_samples(ray_bundle)
-        outputs = self.field(ray_samples)
-        N, S = ray_samples.shape
-        alpha = outputs[FieldHeadNames.ALPHA].reshape(N, S)
-        # _render_weights + AccumulationRenderer + sky fix-up + FeatureRenderer + render_depth_simple, one kernel
-        weights, features, depth, accumulation = F.alpha_composite(
-            alpha, outputs[FieldHeadNames.FEATURE], ray_samples.intervals(), trans_eps=0.0, sky_sample=True
-        )
+        if self.field.can_render(ray_samples):
+            # field + _render_weights + AccumulationRenderer + sky fix-up + FeatureRenderer + render_depth_simple as ONE
+            # autograd node: three kernels forward, three backward, no [N,S,32] gradient tensor
+            weights, features, depth, accumulation = self.field.render(ray_samples, trans_eps=0.0)
+        else:
+            outputs = self.field(ray_samples)
+            N, S = ray_samples.shape
+            alpha = outputs[FieldHeadNames.ALPHA].reshape(N, S)
+            weights, features, depth, accumulation = F.alpha_composite(
+                alpha, outputs[FieldHeadNames.FEATURE], ray_samples.intervals(), trans_eps=0.0, sky_sample=True
+            )
         weights = weights[:, :-1, None]  # the sky sample is discarded for everything downstream (:515)
         nff_outputs = {"features": features, "depth": depth[:, None], "accumulation": accumulation[:, None]}
         for i, (prop_w, prop_rs) in enumerate(zip(proposal_weights, proposal_ray_samples)):

@@ -53,8 +53,8 @@ class _FlatGroup:
             if p.grad is not None:
                 gview.copy_(p.grad)
             p.grad = gview
-            if direct_scatter and p.dim() == 2 and p.numel() >= (1 << 16):
-                p._nrb_grad_sink = gview  # hash tables: the scatter kernels add straight into the flat gradient
+            if direct_scatter:
+                p._nrb_grad_sink = gview  # the backward kernels add straight into the flat gradient
                 if i < n_first:
                     p._nrb_grad_ready = self.reducer.start_early
 

@@ -1,0 +1,68 @@
+"""Import shim for the UNMODIFIED reference modules (test / baseline infrastructure, never imported by the product).
+
+Resolution order: oracle/_ref/ (materialised by oracle/build_ref.py; this is what exists on the GPU box), then the
+read-only checkout (/root/reference or $NEURADAR_REFERENCE; container only).  The reference imports ~25 packages that are
+absent here and are not on the arithmetic path (viewer, plotting, metrics, dataset devkits, nerfacc); they are replaced
+by permissive stub modules so that its fp32 torch path can be executed.
+"""
+import importlib.machinery
+import os
+import sys
+import types
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_CANDIDATES = [os.path.join(HERE, "_ref"), os.environ.get("NEURADAR_REFERENCE", "/root/reference")]
+
+_STUBS = (
+    "viser viser.transforms nerfacc matplotlib matplotlib.pyplot matplotlib.cm plotly plotly.graph_objects "
+    "plotly.express torchmetrics torchmetrics.functional torchmetrics.image torchmetrics.image.lpip pyquaternion "
+    "open3d mediapy splines splines.quaternion gsplat timm pytorch_msssim zod comet_ml av vod pathos git "
+    "sklearn sklearn.neighbors"
+).split()
+
+
+class _Any(types.ModuleType):
+    """A module whose every attribute is again a stub that can be called or used as a base class."""
+
+    def __getattr__(self, name):
+        if name.startswith("__"):
+            raise AttributeError(name)
+        child = _Any(f"{self.__name__}.{name}")
+        child.__spec__ = importlib.machinery.ModuleSpec(child.__name__, None)
+        setattr(self, name, child)
+        sys.modules[child.__name__] = child
+        return child
+
+    def __call__(self, *args, **kwargs):
+        return self
+
+    def __mro_entries__(self, bases):
+        return (object,)
+
+
+def reference_root():
+    for root in _CANDIDATES:
+        if root and os.path.isdir(os.path.join(root, "nerfstudio")):
+            return root
+    return None
+
+
+def available() -> bool:
+    return reference_root() is not None
+
+
+def install() -> str:
+    """Make `import nerfstudio...` resolve to the reference modules; returns the root that was used."""
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference modules not found: run `python oracle/build_ref.py` where /root/reference exists")
+    for name in _STUBS:
+        if name in sys.modules:
+            continue
+        mod = _Any(name)
+        mod.__path__ = []
+        mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        sys.modules[name] = mod
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    return root

@@ -8,59 +8,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 from torch import Tensor
 
+from neuradar_b200.synthetic import build_hot_path, scaled_pixel_area, synthetic_rays  # noqa: F401 (re-exported)
 from oracle import neuradar_oracle as O
-
-
-def synthetic_rays(num_rays: int, seed: int = 42, mix: str = "mixed", device: str = "cpu") -> Dict[str, Tensor]:
-    """Synthetic rays.  mix="mixed": 62.5% camera, 31.25% lidar, 6.25% radar (the reference batch
-    40960/20480/4096 of config 2); mix="radar": 16x16 azimuth x elevation scans of 256 rays."""
-    g = torch.Generator().manual_seed(seed)
-    n = num_rays
-    origins = torch.rand((n, 3), generator=g) * torch.tensor([40.0, 40.0, 3.0]) - torch.tensor([20.0, 20.0, 0.0])
-    d = torch.randn((n, 3), generator=g)
-    directions = d / d.norm(dim=-1, keepdim=True)
-    if mix == "radar":
-        n_radar = n
-    else:
-        n_radar = max((n // 16 // 256) * 256, 0)
-    n_lidar = 0 if mix == "radar" else (n * 5) // 16
-    n_cam = n - n_lidar - n_radar
-    is_lidar = torch.zeros((n, 1), dtype=torch.bool)
-    is_radar = torch.zeros((n, 1), dtype=torch.bool)
-    is_lidar[n_cam : n_cam + n_lidar] = True
-    is_radar[n_cam + n_lidar :] = True
-    if n_radar > 0:
-        scans = n_radar // 256
-        az = torch.arange(16) * 0.0625 - 0.5
-        el = torch.arange(16) * 0.0625 - 0.5
-        azg, elg = torch.meshgrid(az, el, indexing="ij")
-        yaw = torch.rand((max(scans, 1), 1), generator=g) * 2 * math.pi
-        phi = (azg.reshape(1, -1) + yaw).reshape(-1)[:n_radar]
-        theta = elg.reshape(1, -1).expand(max(scans, 1), -1).reshape(-1)[:n_radar]
-        rd = torch.stack([torch.cos(phi) * torch.cos(theta), torch.sin(phi) * torch.cos(theta), torch.sin(theta)], -1)
-        directions[n - n_radar :] = rd
-        origins[n - n_radar :] = origins[n - n_radar :: 256][: max(scans, 1)].repeat_interleave(256, 0)[:n_radar]
-    pixel_area = torch.full((n, 1), 1.0 / 2000.0**2)  # camera; x9 is applied by _scale_pixel_area
-    pixel_area[is_lidar] = 3e-3 * 1.5e-3
-    pixel_area[is_radar] = (0.0625 / 5) ** 2
-    out = dict(
-        origins=origins,
-        directions=directions,
-        pixel_area=pixel_area,
-        nears=torch.zeros((n, 1)),
-        fars=torch.full((n, 1), 1e6),
-        times=torch.rand((n, 1), generator=g) * 20,
-        is_lidar=is_lidar,
-        is_radar=is_radar,
-    )
-    return {k: v.to(device) for k, v in out.items()}
-
-
-def scaled_pixel_area(rays: Dict[str, Tensor], upsample: int = 3) -> Tensor:
-    """pixel_area after NeuRadarModel._scale_pixel_area (models/neuradar.py:996-1008)."""
-    scaling = torch.ones_like(rays["pixel_area"])
-    scaling[~(rays["is_lidar"] | rays["is_radar"])] = upsample**2
-    return rays["pixel_area"] * scaling
 
 
 def make_ray_bundle(rays: Dict[str, Tensor], device: str):
@@ -75,41 +24,6 @@ def make_ray_bundle(rays: Dict[str, Tensor], device: str):
         times=rays["times"].to(device).clone(),
         metadata={"is_lidar": rays["is_lidar"].to(device), "is_radar": rays["is_radar"].to(device)},
     )
-
-
-def build_hot_path(
-    log2_main: int = 19,
-    log2_prop: int = 20,
-    num_proposal_samples: Tuple[int, ...] = (64, 48),
-    num_nerf_samples: int = 48,
-    main_levels: int = 16,
-    main_features: int = 2,
-    main_res: Tuple[int, int] = (16, 1024),
-    late_binding: bool = True,
-    table_gain: Tuple[float, float] = (1.0, 1.0),
-    seed: int = 42,
-    device: str = "cuda",
-):
-    """NeuRadarHotPath in the configuration BASELINE.json names (cfg-A main grid, cfg-P proposal grids)."""
-    import neuradar_b200 as nb
-
-    torch.manual_seed(seed)
-    cfg = nb.NeuRadarHotPathConfig()
-    cfg.late_binding_density_fns = late_binding
-    cfg.sampling.num_proposal_samples = tuple(num_proposal_samples)
-    cfg.sampling.num_nerf_samples = num_nerf_samples
-    cfg.field.grid.static = nb.StaticSettings(
-        hashgrid_dim=main_features, num_levels=main_levels, base_res=main_res[0], max_res=main_res[1],
-        log2_hashmap_size=log2_main,
-    )
-    for p in (cfg.sampling.proposal_field_1, cfg.sampling.proposal_field_2):
-        p.grid.static.log2_hashmap_size = log2_prop
-    model = nb.NeuRadarHotPath(cfg)
-    with torch.no_grad():
-        model.field.hashgrid.static_grid.hash_table.mul_(table_gain[0])
-        for p in model.proposal_fields:
-            p.hashgrid.static_grid.hash_table.mul_(table_gain[1])
-    return model.to(device)
 
 
 def oracle_params(model) -> Tuple[O.FieldParams, List[O.ProposalParams], List[Tensor]]:
