@@ -374,7 +374,7 @@ def run_b200(args, rank, world, local_rank):
     # ---- warm-up (eager), then capture the step in a CUDA graph
     # (on a side stream, as torch's whole-network capture recipe prescribes: autograd's gradient-accumulation nodes stay
     # bound to the stream they were first used on, and that must be the capturing stream)
-    side = torch.cuda.Stream(device=dev)
+    side = torch.cuda.Stream(device=dev, priority=-1)  # above the side streams independent backward branches run on
     load_resident(0)
     side.wait_stream(torch.cuda.current_stream(dev))
     with torch.cuda.stream(side):

@@ -280,6 +280,25 @@ int nrb_accumulate_fwd(const float* weights, const float* values, int64_t N, int
 int nrb_accumulate_bwd(const float* weights, const float* values, const float* dout, int64_t N, int32_t S, int32_t C,
                        float* dweights, float* dvalues, nrb_stream_t stream);
 
+/* ---- per-ray tail: point heads and lidar carving terms ----
+ * Point heads: rendered depth [N] -> one 3-D point per ray.  Rays flagged in is_radar (uint8 [N], may be NULL) use
+ * the spherical direction directions_spher [N,2] = (phi, theta): p = depth (cos phi cos theta, sin phi cos theta,
+ * sin theta) (models/neuradar.py:463-473,1025-1029); all others p = o + d depth (models/ad_model.py:105), optionally
+ * mapped by world2sensor [3,4] row-major (the lidar frame, ad_model.py:103-108).  Backward: ddepth [N] from dpoints. */
+int nrb_point_heads_fwd(const float* origins, const float* directions, const float* depth, const uint8_t* is_radar,
+                        const float* directions_spher, const float* world2sensor, float* points, int64_t N,
+                        nrb_stream_t stream);
+int nrb_point_heads_bwd(const float* directions, const uint8_t* is_radar, const float* directions_spher,
+                        const float* world2sensor, const float* dpoints, float* ddepth, int64_t N, nrb_stream_t stream);
+/* NeuRadarModel._compute_is_close_to_lidar (models/neuradar.py:971-994) and the proposal carving loss (:527-531):
+ * is_close [N,S] (uint8, optional) = for lidar rays |directions_norm - (start+end)/2| < carving_epsilon, or with
+ * did_return (uint8 [N], optional): (did_return & close) | (~did_return & mid < non_return_lidar_distance); false for
+ * other rays.  With weights [N,S] and dloss == NULL: out [N,S] = (w * (is_lidar & ~is_close))^2 (sum it for the loss);
+ * with dloss [1]: out = d loss / d weights = 2 w mask dloss. */
+int nrb_lidar_carving(const nrb_intervals_t* iv, int64_t N, const uint8_t* is_lidar, const float* directions_norm,
+                      const uint8_t* did_return, float carving_epsilon, float non_return_lidar_distance,
+                      const float* weights, const float* dloss, uint8_t* is_close, float* out, nrb_stream_t stream);
+
 /* ---- per-ray training losses on the path's outputs ----
  * MipNeRF-360 distortion loss (nerfstudio/model_components/losses.py:137-156, called on the final level at
  * models/neurad.py via ray_samples.spacing bins): sbins [N,S+1] (row stride bin_stride floats), weights [N,S] ->

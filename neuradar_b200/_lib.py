@@ -152,6 +152,9 @@ SIGNATURES = {
     "nrb_accumulate_fwd": [_P, _P, _I64, _I32, _I32, _P, _P],
     "nrb_accumulate_bwd": [_P, _P, _P, _I64, _I32, _I32, _P, _P, _P],
     "nrb_alpha_composite_bwd": [_P, _P, C.POINTER(Intervals), _I64, _I32, _F, _I32, _P, _P, _P, _P, _P, _P, _P],
+    "nrb_point_heads_fwd": [_P, _P, _P, _P, _P, _P, _P, _I64, _P],
+    "nrb_point_heads_bwd": [_P, _P, _P, _P, _P, _P, _I64, _P],
+    "nrb_lidar_carving": [C.POINTER(Intervals), _I64, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P],
     "nrb_adam_step": [_P, _P, _P, _P, _I64, C.POINTER(AdamCfg), _P, _P, _P, _P],
     "nrb_grad_check": [_P, _I64, _P, _P],
     "nrb_distortion_loss": [_P, _I64, _P, _I64, _I32, _P, _P, _P],

@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kFThreads, 1) field_fused_fwd_kernel(const __g
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kBGroups = 2;
 constexpr int kBWorkers = kBGroups * kRows;  // 256
-constexpr int kBIssuers = 5;                 // weight-gradient issuing warps, one per layer
+constexpr int kBIssuers = 1;                 // one polling warp issues every weight-gradient chain
 constexpr int kBThreads = kBWorkers + kBIssuers * 32;
 // TMEM columns of a group: accumulator [0,32) | A hi [32,56) | A mid [56,80) | delta hi [80,96) | delta mid [96,112)
 constexpr int kBCols = 112;
@@ -422,14 +422,14 @@ __device__ long long g_fused_trace[4096];
   } while (0)
 #define NRB_FTI(slot)                                                                                           \
   do {                                                                                                          \
-    if (blockIdx.x == 0 && uwarp == 8 + 4 && itrace_n < 4000) g_fused_trace[itrace_n++] = (static_cast<long long>(slot) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
+    if (blockIdx.x == 0 && uwarp == 8 && itrace_n < 4000) g_fused_trace[itrace_n++] = (static_cast<long long>(slot) << 48) | (clock64() & 0xFFFFFFFFFFFFll); \
   } while (0)
 #else
 #define NRB_FT(slot)
 #define NRB_FTI(slot)
 #endif
 
-__global__ void __launch_bounds__(kBThreads, 1) field_fused_bwd_kernel(const __grid_constant__ FusedParams prm,
+__global__ void __maxnreg__(128) field_fused_bwd_kernel(const __grid_constant__ FusedParams prm,
                                                                        const __grid_constant__ FusedBwdArgs a,
                                                                        const __grid_constant__ CUtensorMap dfeat_map) {
   extern __shared__ __align__(1024) char smem[];
@@ -491,49 +491,78 @@ __global__ void __launch_bounds__(kBThreads, 1) field_fused_bwd_kernel(const __g
   const int64_t mine = static_cast<int64_t>(blockIdx.x) < tiles ? (tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
   if (uwarp >= 8) {
-    // ---- weight-gradient issuers: warp 8 + l accumulates dW_l (+ db_l) of BOTH groups' tiles, in tile order, so every
-    // accumulator is only ever touched by one issuing thread.  [dW | db | dW'] (+)= delta^T [in hi | 1 | in mid]:
-    // A = delta image (32 hi rows and 32 mid rows = one M = 64 operand), B = the layer's input slot, both MN-major
-    // (reduction over the 128 samples): ONE instruction per 16 samples gives all four partial products.
-    const int l = uwarp - 8;
-    const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(kDwLane[l]) << 16) + static_cast<uint32_t>(kDwCol[l]);
-    const uint32_t idesc = idesc_bf16(64, 2 * kLK[l] + 8, 1, 1);
-    for (int64_t k = 0; k < mine; ++k) {
-      const int gq = static_cast<int>(k & 1);
-      mbar_wait(mb_ready + gq * 5 + l, static_cast<uint32_t>((k >> 1) & 1));
-      if (elect_one()) {
-        NRB_FTI(100 + gq);
-        fence_after_sync();
-        const uint32_t base = smem_u32(smem + gq * FusedBwdSmem::group_bytes);
-        uint64_t da = make_desc(base + FusedBwdSmem::d_hi, 128, 2048), db = make_desc(base + kSlotOff[l], 128, 2048);
+    // ---- the weight-gradient issuer: ONE warp serves the chains of both groups and all layers (each accumulator is only
+    // ever touched by this thread, so the accumulations are ordered).  It polls the two barriers that can fire next - every
+    // group walks its layers 4 -> 0 - and backs off with nanosleep when neither has: the chains are short (8 instructions,
+    // ~0.4 K cycles) and ~11 of them arrive per ~18 K-cycle tile period.
+    // [dW | db | dW'] (+)= delta^T [in hi | 1 | in mid]: A = delta image (32 hi rows and 32 mid rows = one M = 64 operand),
+    // B = the layer's input slot, both MN-major (reduction over the 128 samples): ONE instruction per 16 samples gives
+    // all four partial products.  With 9 warps at <= 128 registers the CTA leaves a quarter of the register file free, so
+    // blocks of the independent proposal-round backward (another stream) co-reside with this latency-bound kernel.
+    const int64_t cnt[2] = {(mine + 1) / 2, mine / 2};
+    int64_t it[2] = {0, 0};
+    int lcur[2] = {4, 4};
+    bool pend[2] = {false, false};  // x image to fetch once dW_4 has consumed g2
+    uint32_t used = 0;              // accumulators that hold a partial sum already
+    while (it[0] < cnt[0] || it[1] < cnt[1] || pend[0] || pend[1]) {
+      bool progressed = false;
 #pragma unroll
-        for (int ks = 0; ks < kRows / 16; ++ks) {  // 16 samples per instruction = two 8-sample groups = 256 bytes
-          mma_bf16_ss(d_tmem, da, db, idesc, k > 0 || ks > 0);
-          da += 16;
-          db += 16;
-        }
-        if (l == 1) {  // the sdf row of W1: the same GEMM with the one-group image (d sdf hi, d sdf mid, 0 ..) as A
-          const uint32_t s_tmem = tmem_base + (static_cast<uint32_t>(kSdfLane) << 16) + static_cast<uint32_t>(kSdfCol);
-          uint64_t sa = make_desc(base + FusedBwdSmem::d_sdf, 128, 2048), sb = make_desc(base + kSlotOff[1], 128, 2048);
-#pragma unroll
-          for (int ks = 0; ks < kRows / 16; ++ks) {
-            mma_bf16_ss(s_tmem, sa, sb, idesc, k > 0 || ks > 0);
-            sa += 16;
-            sb += 16;
+      for (int gq = 0; gq < 2; ++gq) {
+        char* gsq = smem + gq * FusedBwdSmem::group_bytes;
+        if (pend[gq] && mbar_test(mb_done + gq * 5 + 4, static_cast<uint32_t>(it[gq] & 1))) {
+          if (elect_one()) {  // g2 has been consumed: its slot receives the hash-feature image for dW_0 (TMA bulk copy)
+            const int64_t tile = blockIdx.x + (2 * it[gq] + gq) * gridDim.x;
+            mbar_expect_tx(mb_xfull + gq, 16384);
+            bulk_load(gsq + FusedBwdSmem::g2x, a.ximg + tile * 1024, 8192, mb_xfull + gq);
+            bulk_load(gsq + FusedBwdSmem::g2x + 10240, a.ximg + tile * 1024 + 512, 8192, mb_xfull + gq);
           }
+          __syncwarp();
+          pend[gq] = false;
+          progressed = true;
         }
-        mma_commit(mb_done + gq * 5 + l);
-        if (l == 4) {  // once g2 has been consumed its slot receives the hash-feature image for dW_0 (TMA bulk copy)
-          mbar_wait(mb_done + gq * 5 + 4, static_cast<uint32_t>((k >> 1) & 1));
-          char* gsq = smem + gq * FusedBwdSmem::group_bytes;
-          const int64_t tile = blockIdx.x + k * gridDim.x;
-          mbar_expect_tx(mb_xfull + gq, 16384);
-          bulk_load(gsq + FusedBwdSmem::g2x, a.ximg + tile * 1024, 8192, mb_xfull + gq);
-          bulk_load(gsq + FusedBwdSmem::g2x + 10240, a.ximg + tile * 1024 + 512, 8192, mb_xfull + gq);
+        if (it[gq] < cnt[gq] && mbar_test(mb_ready + gq * 5 + lcur[gq], static_cast<uint32_t>(it[gq] & 1))) {
+          const int l = lcur[gq];
+          if (elect_one()) {
+            NRB_FTI(100 + gq);
+            fence_after_sync();
+            const uint32_t base = smem_u32(gsq);
+            const uint32_t d_tmem = tmem_base + (static_cast<uint32_t>(kDwLane[l]) << 16) + static_cast<uint32_t>(kDwCol[l]);
+            const uint32_t idesc = idesc_bf16(64, 2 * kLK[l] + 8, 1, 1);
+            uint64_t da = make_desc(base + FusedBwdSmem::d_hi, 128, 2048), db = make_desc(base + kSlotOff[l], 128, 2048);
+            const bool acc0 = (used >> l) & 1u;
+#pragma unroll
+            for (int ks = 0; ks < kRows / 16; ++ks) {  // 16 samples per instruction = two 8-sample groups = 256 bytes
+              mma_bf16_ss(d_tmem, da, db, idesc, acc0 || ks > 0);
+              da += 16;
+              db += 16;
+            }
+            if (l == 1) {  // the sdf row of W1: the same GEMM with the one-group image (d sdf hi, d sdf mid, 0 ..) as A
+              const uint32_t s_tmem = tmem_base + (static_cast<uint32_t>(kSdfLane) << 16) + static_cast<uint32_t>(kSdfCol);
+              uint64_t sa = make_desc(base + FusedBwdSmem::d_sdf, 128, 2048), sb = make_desc(base + kSlotOff[1], 128, 2048);
+#pragma unroll
+              for (int ks = 0; ks < kRows / 16; ++ks) {
+                mma_bf16_ss(s_tmem, sa, sb, idesc, acc0 || ks > 0);
+                sa += 16;
+                sb += 16;
+              }
+            }
+            mma_commit(mb_done + gq * 5 + l);
+            NRB_FTI(110 + gq);
+          }
+          __syncwarp();
+          used |= 1u << l;
+          if (l == 4) pend[gq] = true;
+          if (l == 0) {
+            lcur[gq] = 4;
+            // (a pending x fetch of this tile was served long ago: dW_0 needs the x image)
+            ++it[gq];
+          } else {
+            lcur[gq] = l - 1;
+          }
+          progressed = true;
         }
-        NRB_FTI(110 + gq);
       }
-      __syncwarp();
+      if (!progressed) __nanosleep(64);
     }
   } else {
     // ---- workers: group g = warps 4g .. 4g+3, thread = sample row r of the group's current tile

@@ -844,6 +844,92 @@ def accumulate(weights: Tensor, values: Optional[Tensor]) -> Tensor:
 
 
 # ------------------------------------------------------------------------------------------------
+# per-ray tail: point heads, lidar carving
+# ------------------------------------------------------------------------------------------------
+def _u8(t: Optional[Tensor]) -> Optional[Tensor]:
+    return None if t is None else t.reshape(-1).to(torch.uint8).contiguous()
+
+
+class _PointHeads(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, depth, origins, directions, is_radar, spher, world2sensor):
+        ctx.depth_shape = depth.shape
+        depth, origins, directions = f32c(depth.reshape(-1)), f32c(origins), f32c(directions)
+        spher = None if spher is None else f32c(spher.reshape(-1, 2))
+        w2s = None if world2sensor is None else f32c(world2sensor[..., :3, :4].reshape(3, 4))
+        N = depth.shape[0]
+        pts = torch.empty((N, 3), device=depth.device, dtype=torch.float32)
+        _lib.call("nrb_point_heads_fwd", ptr(origins), ptr(directions), ptr(depth), ptr(is_radar), ptr(spher), ptr(w2s), ptr(pts), N,
+                  stream_ptr())
+        ctx.save_for_backward(directions, is_radar, spher, w2s)
+        return pts
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dpts):
+        directions, is_radar, spher, w2s = ctx.saved_tensors
+        dpts = f32c(dpts)
+        dd = torch.empty((dpts.shape[0],), device=dpts.device, dtype=torch.float32)
+        _lib.call("nrb_point_heads_bwd", ptr(directions), ptr(is_radar), ptr(spher), ptr(w2s), ptr(dpts), ptr(dd), dpts.shape[0],
+                  stream_ptr())
+        return dd.view(ctx.depth_shape), None, None, None, None, None
+
+
+def point_heads(depth: Tensor, origins: Tensor, directions: Tensor, is_radar: Optional[Tensor] = None,
+                directions_spher: Optional[Tensor] = None, world2sensor: Optional[Tensor] = None) -> Tensor:
+    """Rendered depth [N] / [N,1] -> points [N,3]: lidar / camera rays o + d * depth (optionally in the sensor frame given by
+    world2sensor [3,4] or [4,4]), radar rays depth * unit(phi, theta) from directions_spher [N,2].  Differentiable in depth."""
+    return _PointHeads.apply(depth, origins, directions, _u8(is_radar), directions_spher, world2sensor)
+
+
+class _CarvingLoss(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, weights, iv: SampleIntervals, is_lidar, dir_norm, did_return, eps: float, max_dist: float):
+        w = f32c(weights)
+        N, S = w.shape
+        out = torch.empty_like(w)
+        i = iv.struct()
+        _lib.call("nrb_lidar_carving", C.byref(i), N, ptr(is_lidar), ptr(dir_norm), ptr(did_return), float(eps), float(max_dist),
+                  ptr(w), None, None, ptr(out), stream_ptr())
+        ctx.save_for_backward(w, is_lidar, dir_norm, did_return)
+        ctx.iv, ctx.eps, ctx.max_dist = iv, float(eps), float(max_dist)
+        return out.sum()
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dloss):
+        w, is_lidar, dir_norm, did_return = ctx.saved_tensors
+        dw = torch.empty_like(w)
+        i = ctx.iv.struct()
+        dl = f32c(dloss.reshape(1))
+        _lib.call("nrb_lidar_carving", C.byref(i), w.shape[0], ptr(is_lidar), ptr(dir_norm), ptr(did_return), ctx.eps, ctx.max_dist,
+                  ptr(w), ptr(dl), None, ptr(dw), stream_ptr())
+        return dw, None, None, None, None, None, None
+
+
+def is_close_to_lidar(iv: SampleIntervals, is_lidar: Tensor, directions_norm: Tensor, did_return: Optional[Tensor] = None,
+                      carving_epsilon: float = 0.1, non_return_lidar_distance: float = 150.0) -> Tensor:
+    """NeuRadarModel._compute_is_close_to_lidar for the samples `iv` of N rays: bool [N,S]."""
+    N, S = iv.starts.shape[0], iv.num_samples
+    out = torch.empty((N, S), device=iv.starts.device, dtype=torch.uint8)
+    i = iv.struct()
+    lid, dn, ret = _u8(is_lidar), f32c(directions_norm.reshape(-1)), _u8(did_return)  # kept alive across the launch
+    _lib.call("nrb_lidar_carving", C.byref(i), N, ptr(lid), ptr(dn), ptr(ret), float(carving_epsilon),
+              float(non_return_lidar_distance), None, None, ptr(out), None, stream_ptr())
+    return out.bool()
+
+
+def carving_loss(weights: Tensor, iv: SampleIntervals, is_lidar: Tensor, directions_norm: Tensor,
+                 did_return: Optional[Tensor] = None, carving_epsilon: float = 0.1,
+                 non_return_lidar_distance: float = 150.0) -> Tensor:
+    """sum((weights * (is_lidar & ~is_close_to_lidar))^2) over weights [N,S] (models/neuradar.py:527-531), one kernel each way."""
+    return _CarvingLoss.apply(weights, iv, _u8(is_lidar), f32c(directions_norm.reshape(-1)), _u8(did_return), carving_epsilon,
+                              non_return_lidar_distance)
+
+
+# ------------------------------------------------------------------------------------------------
 # fused proposal round
 # ------------------------------------------------------------------------------------------------
 class _ProposalRound(torch.autograd.Function):

@@ -7,6 +7,7 @@ lidar MLP, radar transformer) stay in PyTorch upstream of this module and are ou
 """
 from __future__ import annotations
 
+import dataclasses
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
@@ -42,6 +43,14 @@ class SamplingSettings:
 
 
 @dataclass
+class LossSettings:
+    """The two loss settings the path itself reads (models/neurad.py:79,87)."""
+
+    carving_epsilon: float = 0.1
+    non_return_lidar_distance: float = 150.0
+
+
+@dataclass
 class NeuRadarHotPathConfig:
     sampling: SamplingSettings = field(default_factory=SamplingSettings)
     field: NeuRADFieldConfig = field(default_factory=NeuRADFieldConfig)
@@ -50,6 +59,16 @@ class NeuRadarHotPathConfig:
     late_binding_density_fns: bool = True
     """Reproduce the reference's late-binding lambda list (models/neuradar.py:302): every proposal round queries
     the LAST proposal field.  False gives each round its own field."""
+    loss: "LossSettings" = dataclasses.field(default_factory=lambda: LossSettings())
+    appearance_dim: int = 0
+    """> 0 adds the per-sensor appearance code to the rendered features (models/neuradar.py:205-215,510-512)."""
+    num_sensors: int = 1
+    use_temporal_appearance: bool = False
+    num_embeds_per_sensor: int = 1
+    sequence_duration: float = 1.0
+    gather_non_nearby: bool = False
+    """Also emit `non_nearby_weights` / `non_nearby_lidar_ray_indices` exactly as the reference does (a nonzero()
+    gather, i.e. a host synchronisation); `non_nearby_mask` and `non_nearby_weights_sq_sum` are always there."""
 
 
 class DensityFn:
@@ -86,6 +105,9 @@ class NeuRadarHotPath(nn.Module):
         else:
             self.density_fns = [DensityFn(f) for f in self.proposal_fields]
         self.field: NeuRADField = config.field.setup(actors=actors, static_scale=config.static_scale)
+        self.appearance_embedding = None
+        if config.appearance_dim > 0:
+            self.appearance_embedding = nn.Embedding(config.num_sensors * config.num_embeds_per_sensor, config.appearance_dim)
 
     def get_param_groups(self) -> Dict[str, List[nn.Parameter]]:
         groups: Dict[str, List[nn.Parameter]] = {"hashgrids": [], "fields": []}
@@ -142,13 +164,72 @@ class NeuRadarHotPath(nn.Module):
             )
         weights = weights[:, :-1, None]  # the sky sample is discarded for everything downstream (:515)
         nff_outputs = {"features": features, "depth": depth[:, None], "accumulation": accumulation[:, None]}
+        if self.appearance_embedding is not None:  # models/neuradar.py:510-512,550-568
+            nff_outputs["features"] = torch.cat([features, self._get_appearance_embedding(ray_bundle, features)], dim=-1)
+        md = ray_bundle.metadata or {}
+        carve = self.training and calc_lidar_losses and "is_lidar" in md and "directions_norm" in md
+        lc = self.config.loss
         for i, (prop_w, prop_rs) in enumerate(zip(proposal_weights, proposal_ray_samples)):
             steps = (prop_rs.frustums.starts + prop_rs.frustums.ends) / 2
             nff_outputs[f"prop_depth_{i}"] = F.accumulate(prop_w[..., 0], steps)
+            if carve:  # carving loss of the proposal rounds (:529-531): sum((w * (is_lidar & ~is_close_to_lidar))^2)
+                nff_outputs[f"prop_weights_loss_{i}"] = F.carving_loss(
+                    prop_w[..., 0], prop_rs.intervals(), md["is_lidar"], md["directions_norm"], md.get("did_return"),
+                    lc.carving_epsilon, lc.non_return_lidar_distance)
         if self.training:
             nff_outputs["weights_list"] = proposal_weights + [weights]
             nff_outputs["ray_samples_list"] = proposal_ray_samples + [ray_samples[..., :-1]]
+        if carve:  # :537-546
+            iv = F.SampleIntervals(ray_samples.frustums.starts[:, :-1], ray_samples.frustums.ends[:, :-1])
+            close = F.is_close_to_lidar(iv, md["is_lidar"], md["directions_norm"], md.get("did_return"), lc.carving_epsilon,
+                                        lc.non_return_lidar_distance)
+            mask = (~close) & md["is_lidar"].reshape(-1, 1).bool()
+            nff_outputs["non_nearby_mask"] = mask
+            # the sum of squares the reference forms from the gathered weights (:638), without the nonzero() round trip
+            nff_outputs["non_nearby_weights_sq_sum"] = F.carving_loss(
+                weights[..., 0], iv, md["is_lidar"], md["directions_norm"], md.get("did_return"), lc.carving_epsilon,
+                lc.non_return_lidar_distance)
+            if self.config.gather_non_nearby:  # exactly the reference's outputs; nonzero() synchronises the host
+                idx = mask.nonzero(as_tuple=True)
+                nff_outputs["non_nearby_weights"] = weights[..., 0][idx][:, None]
+                lidar_start = md["is_lidar"].reshape(-1).int().argmax()
+                nff_outputs["non_nearby_lidar_ray_indices"] = (idx[0] - lidar_start)[:, None]
         return nff_outputs
+
+    def _get_appearance_embedding(self, ray_bundle: RayBundle, features: Tensor) -> Tensor:
+        """models/neuradar.py:550-568: per-sensor (optionally time-interpolated) appearance code."""
+        c = self.config
+        sensor_idx = (ray_bundle.metadata or {}).get("sensor_idxs")
+        if sensor_idx is None:
+            assert not self.training, "Sensor sensor_idx must be present in metadata during training"
+            sensor_idx = torch.zeros_like(features[..., :1], dtype=torch.long)
+        if c.use_temporal_appearance:
+            n_e = c.num_embeds_per_sensor
+            time_idx = ray_bundle.times / c.sequence_duration * n_e
+            before = time_idx.floor().clamp(0, n_e - 1)
+            after = (before + 1).clamp(0, n_e - 1)
+            ratio = time_idx - before
+            before, after = (x + sensor_idx * n_e for x in (before, after))
+            return (self.appearance_embedding(before.squeeze(-1).long()) * (1 - ratio)
+                    + self.appearance_embedding(after.squeeze(-1).long()) * ratio)
+        return self.appearance_embedding(sensor_idx.squeeze(-1))
+
+    def point_heads(self, ray_bundle: RayBundle, depth: Tensor, world2lidar: Optional[Tensor] = None) -> Dict[str, Tensor]:
+        """The point heads on a rendered depth [N,1]: `points` for lidar / camera rays = o + d * depth,
+        in the lidar frame when world2lidar is given (models/ad_model.py:103-108); for the rays flagged is_radar the
+        cartesian position from the spherical direction (models/neuradar.py:463-473,1025-1029) that feeds the radar
+        decoder's positional embedding.  One kernel, differentiable in depth."""
+        md = ray_bundle.metadata or {}
+        is_radar = md.get("is_radar")
+        spher = md.get("directions_spher")
+        if is_radar is not None and spher is None:
+            is_radar = None
+        pts = F.point_heads(depth, ray_bundle.origins.reshape(-1, 3), ray_bundle.directions.reshape(-1, 3), is_radar, spher,
+                            world2lidar)
+        out = {"points": pts}
+        if is_radar is not None:
+            out["radar_xyz"] = pts[is_radar.reshape(-1)]
+        return out
 
     def forward(self, ray_bundle: RayBundle) -> Dict[str, Tensor]:
         return self.get_nff_outputs(ray_bundle)

@@ -432,6 +432,26 @@ def radar_points(depth: Tensor, theta: Tensor, phi: Tensor) -> Tensor:
     return torch.cat((x, y, z), dim=-1)
 
 
+def is_close_to_lidar(starts: Tensor, ends: Tensor, is_lidar: Tensor, directions_norm: Tensor,
+                      did_return: Optional[Tensor] = None, carving_epsilon: float = 0.1,
+                      non_return_lidar_distance: float = 150.0) -> Tensor:
+    """`NeuRadarModel._compute_is_close_to_lidar` (models/neuradar.py:971-994) restated densely: starts / ends [N,S],
+    is_lidar / did_return [N,1] bool, directions_norm [N,1]; returns bool [N,S] (False for every non-lidar ray)."""
+    mid = (starts + ends) * 0.5
+    close_to_hit = (directions_norm - mid).abs() < carving_epsilon
+    if did_return is not None:
+        in_range = mid < non_return_lidar_distance
+        close = (did_return & close_to_hit) | ((~did_return) & in_range)
+    else:
+        close = close_to_hit
+    return close & is_lidar
+
+
+def carving_loss(weights: Tensor, close: Tensor, is_lidar: Tensor) -> Tensor:
+    """`((prop_w * weights_mask) ** 2).sum()` with weights_mask = ~is_close_to_lidar & is_lidar (models/neuradar.py:529-531)."""
+    return ((weights * ((~close) & is_lidar)) ** 2).sum()
+
+
 # --------------------------------------------------------------------------------------------
 # the whole path: NeuRadarModel._get_ray_samples + get_nff_outputs
 # --------------------------------------------------------------------------------------------

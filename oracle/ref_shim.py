@@ -39,6 +39,9 @@ class _Any(types.ModuleType):
     def __mro_entries__(self, bases):
         return (object,)
 
+    def __getitem__(self, item):  # used as a generic in annotations
+        return self
+
 
 def reference_root():
     for root in _CANDIDATES:
@@ -63,6 +66,9 @@ def install() -> str:
         mod.__path__ = []
         mod.__spec__ = importlib.machinery.ModuleSpec(name, None)
         sys.modules[name] = mod
+    import typing
+
+    sys.modules["git"].Optional = typing.Optional  # model_components/radar_utils.py:20 imports typing.Optional through GitPython
     if root not in sys.path:
         sys.path.insert(0, root)
     return root

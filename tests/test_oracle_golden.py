@@ -257,3 +257,39 @@ def test_adam_step_matches_torch_optim(decoupled, wd):
     st = opt.state[ref_p]
     torch.testing.assert_close(m, st["exp_avg"], rtol=1e-6, atol=1e-12)
     torch.testing.assert_close(v, st["exp_avg_sq"], rtol=1e-6, atol=1e-20)
+
+
+def test_is_close_to_lidar_matches_reference_method():
+    """oracle.is_close_to_lidar against the reference's own NeuRadarModel._compute_is_close_to_lidar (executed from
+    oracle/_ref or the checkout; skipped where neither exists)."""
+    import types
+
+    from oracle import ref_shim
+
+    if not ref_shim.available():
+        pytest.skip("reference modules not available")
+    ref_shim.install()
+    from nerfstudio.cameras.rays import Frustums, RaySamples
+    from nerfstudio.models.neuradar import NeuRadarModel
+
+    g = torch.Generator().manual_seed(11)
+    n, S = 40, 16
+    bins = torch.cumsum(torch.rand((n, S + 1), generator=g) * 20, dim=-1)
+    is_lidar = (torch.arange(n) % 2 == 0)[:, None]
+    dnorm = torch.rand((n, 1), generator=g) * float(bins.max())
+    dnorm[::4] = ((bins[::4, 3] + bins[::4, 4]) * 0.5 + 0.05)[:, None]
+    did_return = torch.rand((n, 1), generator=g) > 0.3
+    for use_return in (True, False):
+        md = {"is_lidar": is_lidar[:, None, :].expand(n, S, 1), "directions_norm": dnorm[:, None, :].expand(n, S, 1)}
+        if use_return:
+            md["did_return"] = did_return[:, None, :].expand(n, S, 1)
+        fr = Frustums(origins=torch.zeros((n, S, 3)), directions=torch.zeros((n, S, 3)), starts=bins[:, :-1, None].clone(),
+                      ends=bins[:, 1:, None].clone(), pixel_area=torch.ones((n, S, 1)))
+        rs = RaySamples(frustums=fr, metadata=md)
+        fake_self = types.SimpleNamespace(config=types.SimpleNamespace(loss=types.SimpleNamespace(
+            carving_epsilon=0.1, non_return_lidar_distance=150.0)))
+        NeuRadarModel._compute_is_close_to_lidar(fake_self, rs)
+        want = rs.metadata["is_close_to_lidar"][..., 0]
+        got = O.is_close_to_lidar(bins[:, :-1], bins[:, 1:], is_lidar, dnorm, did_return if use_return else None)
+        assert torch.equal(got, want)
+        assert bool(want.any()) and not bool(want.all())
