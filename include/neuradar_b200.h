@@ -33,6 +33,7 @@ extern "C" {
 #define NRB_MAX_MLP_LAYERS 4
 #define NRB_MAX_MLP_WIDTH 64
 #define NRB_MAX_SAMPLES 256 /* samples per ray handled by the warp-per-ray kernels */
+#define NRB_MAX_ACTORS 32   /* per-actor hash grids handled by the fused kernels */
 
 typedef void* nrb_stream_t; /* cudaStream_t */
 
@@ -186,10 +187,30 @@ typedef struct {
   uint32_t* masks;
   int64_t ld;
 } nrb_field_fused_saved_t;
+/* Dynamic actors (NeuRADHashEncoding's actor branch on the torch path: one 3-D grid per actor,
+ * neurad_encoding.py:112-119,295-307).  tables[i] = actor_grids.i.hash_table [4 * 2^log2_hashmap_size, 4]; scalings = the
+ * four level resolutions.  The per-sample assignment comes from nrb_actor_assign: grid_id [M] (-1 = static world), pos
+ * [M,3] in the grid's unit cube, std [M], dirs [M,3] (view direction in the actor frame).  Samples with grid_id >= 0 take
+ * their 16 features from that grid (zero-padded to 32, neurad_encoding.py:181-187) and the SH basis of dirs. */
+typedef struct {
+  const float* tables[NRB_MAX_ACTORS];
+  float scalings[NRB_MAX_LEVELS];
+  int32_t num_levels;         /* 4 */
+  int32_t features_per_level; /* 4 */
+  int32_t log2_hashmap_size;
+  int32_t num_grids;
+} nrb_actor_grids_t;
+typedef struct {
+  const int32_t* grid_id;
+  const float* pos;
+  const float* std;
+  const float* dirs;
+} nrb_actor_samples_t;
 int64_t nrb_field_fused_image_bytes(int64_t M);
 int nrb_field_fused_fwd(const nrb_field_mlp_t* mlp, const nrb_grid_t* grid, const float* xyz, const float* std,
                         const float* x, const float* sh, int32_t samples_per_ray, int64_t M, float* feature, float* sdf,
-                        float* alpha, const nrb_field_fused_saved_t* saved, nrb_stream_t stream);
+                        float* alpha, const nrb_field_fused_saved_t* saved, const nrb_actor_grids_t* actor_grids,
+                        const nrb_actor_samples_t* actor_samples, nrb_stream_t stream);
 /* Backward.  The gradient of the feature output is EITHER dfeature [M,32] OR - with the compositor folded in
  * (sum_s w f, models/neuradar.py:509) - its factors dfeat_ray [rays,32] and weights [M]: dfeature[m] = weights[m] *
  * dfeat_ray[m / samples_per_ray].  dsdf / dalpha [M] are optional.  dximg (optional) receives the gradient with
@@ -207,6 +228,8 @@ typedef struct {
   const float* weights;
   const float* dsdf;
   const float* dalpha;
+  const int32_t* actor_grid_id; /* optional, with actor_dirs: the per-sample assignment of the forward */
+  const float* actor_dirs;
 } nrb_field_fused_bwd_in_t;
 typedef struct {
   float* dximg;
@@ -216,9 +239,25 @@ typedef struct {
 } nrb_field_fused_bwd_out_t;
 int nrb_field_fused_bwd(const nrb_field_mlp_t* mlp, const nrb_field_fused_bwd_in_t* in,
                         const nrb_field_fused_bwd_out_t* out, int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
-/* nrb_hash_bwd for a data gradient in the tile-image layout above (32 features per sample). */
+/* nrb_hash_bwd for a data gradient in the tile-image layout above (32 features per sample); samples whose
+ * actor_grid_id (optional) is >= 0 are skipped: their features came from an actor grid. */
 int nrb_hash_bwd_image(const nrb_grid_t* grid, const float* x, const float* std, const float* dyimg, float* dtable,
-                       int64_t M, void* workspace, int64_t workspace_bytes, nrb_stream_t stream);
+                       const int32_t* actor_grid_id, int64_t M, void* workspace, int64_t workspace_bytes,
+                       nrb_stream_t stream);
+/* ---- dynamic actors as kernels (neurad_encoding.py:176-275) ----
+ * Per sample of (rays, iv): exact box test against every valid actor of the ray - world2boxes [N,A,3,4] row-major (the
+ * inverse of DynamicActors.get_boxes2world, dynamic_actors.py:183-197), valid [N,A] uint8, bounds [A,3] half extents -
+ * then the box-frame gaussian contracted with actor_scale, the rotated and normalised view direction, and the optional
+ * per-ray mirror flip [N] (+1 / -1, training).  Outputs as nrb_actor_samples_t plus the optional actor_index [M] (index
+ * into the ray's actor list).  No compaction, no host synchronisation. */
+int nrb_actor_assign(const nrb_rays_t* rays, const nrb_intervals_t* iv, const float* world2boxes, const uint8_t* valid,
+                     const float* bounds, const int32_t* actor_to_id, int32_t num_actors, const float* flip,
+                     float actor_scale, int32_t* grid_id, float* pos, float* std, float* dirs, int32_t* actor_index,
+                     nrb_stream_t stream);
+/* Scatter of the actor samples' feature gradient (tile image, features 0..15) into dtables[grid] (accumulated); dpos
+ * [M,3] (optional) receives the gradient with respect to pos. */
+int nrb_actor_scatter(const nrb_actor_grids_t* grids, float* const* dtables, const nrb_actor_samples_t* samples,
+                      const float* dyimg, float* dpos, int64_t M, nrb_stream_t stream);
 
 /* Debug probe of the UMMA descriptor conventions: P, Q [128,32] are staged as canonical tiles, a chain of tf32 MMAs
  * is issued with cfg = {a_major, b_major, M, N, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps} (host ints) and the

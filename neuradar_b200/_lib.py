@@ -98,8 +98,21 @@ class FieldFusedSaved(C.Structure):  # nrb_field_fused_saved_t
 
 class FieldFusedBwdIn(C.Structure):
     _fields_ = [("saved", FieldFusedSaved)] + [
-        (n, C.c_void_p) for n in ("sh", "sdf", "alpha", "dfeature", "dfeat_ray", "weights", "dsdf", "dalpha")
+        (n, C.c_void_p) for n in ("sh", "sdf", "alpha", "dfeature", "dfeat_ray", "weights", "dsdf", "dalpha", "actor_grid_id",
+                                  "actor_dirs")
     ]
+
+
+MAX_ACTORS = 32
+
+
+class ActorGrids(C.Structure):  # nrb_actor_grids_t
+    _fields_ = [("tables", C.c_void_p * MAX_ACTORS), ("scalings", C.c_float * MAX_LEVELS), ("num_levels", C.c_int32),
+                ("features_per_level", C.c_int32), ("log2_hashmap_size", C.c_int32), ("num_grids", C.c_int32)]
+
+
+class ActorSamples(C.Structure):  # nrb_actor_samples_t
+    _fields_ = [("grid_id", C.c_void_p), ("pos", C.c_void_p), ("std", C.c_void_p), ("dirs", C.c_void_p)]
 
 
 class FieldFusedBwdOut(C.Structure):
@@ -141,9 +154,11 @@ SIGNATURES = {
     "nrb_tc_probe": [_P, _P, C.POINTER(C.c_int32), _P, _P],
     "nrb_field_fused_image_bytes": [_I64],
     "nrb_field_fused_fwd": [C.POINTER(FieldMlp), C.POINTER(Grid), _P, _P, _P, _P, _I32, _I64, _P, _P, _P,
-                            C.POINTER(FieldFusedSaved), _P],
+                            C.POINTER(FieldFusedSaved), C.POINTER(ActorGrids), C.POINTER(ActorSamples), _P],
     "nrb_field_fused_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldFusedBwdIn), C.POINTER(FieldFusedBwdOut), _I32, _I64, _P],
-    "nrb_hash_bwd_image": [C.POINTER(Grid), _P, _P, _P, _P, _I64, _P, _I64, _P],
+    "nrb_hash_bwd_image": [C.POINTER(Grid), _P, _P, _P, _P, _P, _I64, _P, _I64, _P],
+    "nrb_actor_assign": [C.POINTER(Rays), C.POINTER(Intervals), _P, _P, _P, _P, _I32, _P, _F, _P, _P, _P, _P, _P, _P],
+    "nrb_actor_scatter": [C.POINTER(ActorGrids), C.POINTER(C.c_void_p), C.POINTER(ActorSamples), _P, _P, _I64, _P],
     "nrb_spaced_bins": [C.POINTER(Rays), Spacing, _P, _P, _I32, _I32, _P, _P, _P],
     "nrb_pdf_sample": [C.POINTER(Rays), Spacing, _P, _P, _I32, _P, _P, _I32, _F, _F, _P, _P, _P, _P, _P],
     "nrb_density_weights_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],

@@ -52,17 +52,9 @@ struct Gaussian {
   float std;      // contracted standard deviation
 };
 
-// Frustums.get_fast_isotropic_gaussian(1) (cameras/rays.py:109-124) then ScaledSceneContraction(inf, scale) on
-// GaussiansStd with normalize=True (spatial_distortions.py:103-113,132-136).
-__device__ __forceinline__ Gaussian sample_gaussian(float ox, float oy, float oz, float dx, float dy, float dz,
-                                                    float pixel_area, float start, float end, float scale) {
-  const float dist = mul(sub(end, start), 0.5f);
-  const float t = add(start, dist);
-  float mx = add(ox, mul(dx, t));
-  float my = add(oy, mul(dy, t));
-  float mz = add(oz, mul(dz, t));
-  const float area = mul(pixel_area, mul(t, t));
-  float std = powf(mul(area, dist), kThird);
+// ScaledSceneContraction(order=inf, scale) on GaussiansStd with normalize=True (spatial_distortions.py:103-113,132-136):
+// world-space mean / std -> the hash grid's unit cube.
+__device__ __forceinline__ Gaussian contract_gaussian(float mx, float my, float mz, float std, float scale) {
   mx = div(mx, scale);
   my = div(my, scale);
   mz = div(mz, scale);
@@ -83,6 +75,27 @@ __device__ __forceinline__ Gaussian sample_gaussian(float ox, float oy, float oz
   g.z = mul(add(mz, 2.0f), 0.25f);
   g.std = mul(std, 0.25f);
   return g;
+}
+
+// Frustums.get_fast_isotropic_gaussian(1) (cameras/rays.py:109-124): world-space mean and standard deviation of a sample
+__device__ __forceinline__ Gaussian world_gaussian(float ox, float oy, float oz, float dx, float dy, float dz,
+                                                   float pixel_area, float start, float end) {
+  const float dist = mul(sub(end, start), 0.5f);
+  const float t = add(start, dist);
+  Gaussian g;
+  g.x = add(ox, mul(dx, t));
+  g.y = add(oy, mul(dy, t));
+  g.z = add(oz, mul(dz, t));
+  const float area = mul(pixel_area, mul(t, t));
+  g.std = powf(mul(area, dist), kThird);
+  return g;
+}
+
+// ... followed by the contraction
+__device__ __forceinline__ Gaussian sample_gaussian(float ox, float oy, float oz, float dx, float dy, float dz,
+                                                    float pixel_area, float start, float end, float scale) {
+  const Gaussian w = world_gaussian(ox, oy, oz, dx, dy, dz, pixel_area, start, end);
+  return contract_gaussian(w.x, w.y, w.z, w.std, scale);
 }
 
 // 1 / max(1, 2*scal*std): neurad_encoding.py:314  ((scalings * 2) * std).clamp_min(1)

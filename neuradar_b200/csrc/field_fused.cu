@@ -35,6 +35,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include "actor_grid.cuh"
 #include "hash_bwd_plan.cuh"
 #include "tc_common.cuh"
 
@@ -149,9 +150,11 @@ struct FusedFwdArgs {
   uint4* ximg;        // training: bf16 hi / mid operand image of the hash features, 16 KB per tile
   uint32_t* masks;    // training: [3][ld] ReLU bit masks of h1, g1, g2
   int64_t ld;
+  ActorGridsDev ag;   // kActors: per-actor tables and the per-sample assignment (actors.cu)
+  ActorSamplesDev as;
 };
 
-template <int F>
+template <int F, bool kActors>
 __global__ void __launch_bounds__(kFThreads, 1) field_fused_fwd_kernel(const __grid_constant__ FusedParams prm,
                                                                        const __grid_constant__ GridDev grid,
                                                                        const __grid_constant__ FusedFwdArgs a) {
@@ -208,7 +211,20 @@ __global__ void __launch_bounds__(kFThreads, 1) field_fused_fwd_kernel(const __g
     // All 32 values are produced before anything is staged so that the compiler can keep the gathers of several levels
     // in flight (the tensor-memory stores below are ordering points for it).
     float v[32];
-    if constexpr (F > 0) {
+    int agid = -1;  // actor grid of this sample (-1: static world)
+    if constexpr (kActors) agid = __ldg(a.as.grid_id + rr);
+    if (kActors && agid >= 0) {
+      // a sample inside an actor box: 16 features of that actor's grid, zero-padded, replace the static ones
+      // (neurad_encoding.py:181-187)
+      float o16[16];
+      actor_gather16(a.ag, agid, __ldg(a.as.pos + 3 * rr), __ldg(a.as.pos + 3 * rr + 1), __ldg(a.as.pos + 3 * rr + 2),
+                     __ldg(a.as.std + rr), o16);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        v[j] = o16[j];
+        v[16 + j] = 0.0f;
+      }
+    } else if constexpr (F > 0) {
       const float px = __ldg(a.xyz + 3 * rr), py = __ldg(a.xyz + 3 * rr + 1), pz = __ldg(a.xyz + 3 * rr + 2);
       const float sd = a.std != nullptr ? __ldg(a.std + rr) : 0.0f;
       const uint32_t hmask = (1u << grid.log2_size) - 1u;
@@ -289,14 +305,18 @@ __global__ void __launch_bounds__(kFThreads, 1) field_fused_fwd_kernel(const __g
     tmem_store_row_split<32>(tg, uwarp, kFAHi, kFALo, 0, emb);
     {
       float shv[16];
-      const float4* shp = reinterpret_cast<const float4*>(a.sh + (rr / a.samples_per_ray) * 16);
+      if (kActors && agid >= 0) {  // the view direction was rotated into the actor's frame: its own SH basis
+        sh16_of_direction(__ldg(a.as.dirs + 3 * rr), __ldg(a.as.dirs + 3 * rr + 1), __ldg(a.as.dirs + 3 * rr + 2), shv);
+      } else {
+        const float4* shp = reinterpret_cast<const float4*>(a.sh + (rr / a.samples_per_ray) * 16);
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float4 q4 = __ldg(shp + c);
-        shv[4 * c] = q4.x;
-        shv[4 * c + 1] = q4.y;
-        shv[4 * c + 2] = q4.z;
-        shv[4 * c + 3] = q4.w;
+        for (int c = 0; c < 4; ++c) {
+          const float4 q4 = __ldg(shp + c);
+          shv[4 * c] = q4.x;
+          shv[4 * c + 1] = q4.y;
+          shv[4 * c + 2] = q4.z;
+          shv[4 * c + 3] = q4.w;
+        }
       }
       tmem_store_row_split<16>(tg, uwarp, kFAHi, kFALo, 32, shv);
     }
@@ -389,6 +409,8 @@ struct FusedBwdArgs {
   const float* dalpha;     // [M] or null
   int samples_per_ray;
   int64_t M;
+  const int32_t* actor_grid_id;  // [M] or null: samples >= 0 use their own direction's SH basis
+  const float* actor_dirs;       // [M,3]
   float4* dximg;           // [tiles][8 chunks][128 rows] float4, or null
   float* dw[5];
   float* db[5];
@@ -686,7 +708,12 @@ __global__ void __maxnreg__(128) field_fused_bwd_kernel(const __grid_constant__ 
       const uint32_t mh1 = m_h1, mg1 = m_g1, mg2 = m_g2;
       // the ray's SH basis (inputs 32..47 of layer 2), requested two layers before it is used
       float4 shq[4];
-      {
+      if (a.actor_grid_id != nullptr && __ldg(a.actor_grid_id + rc) >= 0) {
+        float o[16];
+        sh16_of_direction(__ldg(a.actor_dirs + 3 * rc), __ldg(a.actor_dirs + 3 * rc + 1), __ldg(a.actor_dirs + 3 * rc + 2), o);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) shq[c] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      } else {
         const float4* shp = reinterpret_cast<const float4*>(a.sh + (rc / a.samples_per_ray) * 16);
 #pragma unroll
         for (int c = 0; c < 4; ++c) shq[c] = __ldg(shp + c);
@@ -912,14 +939,15 @@ __global__ void __launch_bounds__(256) hash_bwd_img_kernel(const __grid_constant
                                                            const __grid_constant__ BwdPlan plan,
                                                            const float* __restrict__ x, const float* __restrict__ std,
                                                            const float* __restrict__ dyimg, float* __restrict__ dtable,
-                                                           int64_t M) {
+                                                           const int32_t* __restrict__ actor_grid_id, int64_t M) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int L = g.num_levels;
   const int64_t base = (static_cast<int64_t>(blockIdx.x) * 8 + warp) * 32;
   if (base >= M) return;
   const int64_t m = base + lane;
-  const bool valid = m < M;
-  const int64_t mc = valid ? m : (M - 1);
+  const int64_t mc = m < M ? m : (M - 1);
+  // samples claimed by an actor grid took none of their features from this table
+  const bool valid = m < M && (actor_grid_id == nullptr || __ldg(actor_grid_id + mc) < 0);
   const float px = __ldg(x + 3 * mc), py = __ldg(x + 3 * mc + 1), pz = __ldg(x + 3 * mc + 2);
   const float sd = std != nullptr ? __ldg(std + mc) : 0.0f;
   const float* row = dyimg + ((m >> 7) * 1024 + (m & 127)) * 4;  // chunk c of this sample at row + c * 512 floats
@@ -1000,7 +1028,9 @@ extern "C" int64_t nrb_field_fused_image_bytes(int64_t M) { return (M + tc::kRow
 
 extern "C" int nrb_field_fused_fwd(const nrb_field_mlp_t* p, const nrb_grid_t* grid, const float* xyz, const float* std,
                                    const float* x, const float* sh, int32_t samples_per_ray, int64_t M, float* feature,
-                                   float* sdf, float* alpha, const nrb_field_fused_saved_t* saved, nrb_stream_t stream) {
+                                   float* sdf, float* alpha, const nrb_field_fused_saved_t* saved,
+                                   const nrb_actor_grids_t* actor_grids, const nrb_actor_samples_t* actor_samples,
+                                   nrb_stream_t stream) {
   NRB_REQUIRE(p && sh && feature && sdf && alpha && M >= 0 && samples_per_ray > 0, NRB_ERR_BAD_ARG,
               "nrb_field_fused_fwd: null pointer or bad size");
   for (int l = 0; l < 5; ++l) NRB_REQUIRE(p->weights[l] != nullptr, NRB_ERR_BAD_ARG, "nrb_field_fused_fwd: weights[%d] is null", l);
@@ -1029,16 +1059,26 @@ extern "C" int nrb_field_fused_fwd(const nrb_field_mlp_t* p, const nrb_grid_t* g
                 NRB_ERR_BAD_ARG, "nrb_field_fused_fwd: saved.masks / saved.ld (nrb_field_saved_ld(M)) / alignment");
     a.ximg = static_cast<uint4*>(saved->ximg), a.masks = saved->masks, a.ld = saved->ld;
   }
+  const bool actors = actor_grids != nullptr;
+  if (actors) {
+    if (int rc = check_actor_grids("nrb_field_fused_fwd", actor_grids)) return rc;
+    NRB_REQUIRE(grid != nullptr && actor_samples && actor_samples->grid_id && actor_samples->pos && actor_samples->std &&
+                    actor_samples->dirs,
+                NRB_ERR_BAD_ARG, "nrb_field_fused_fwd: actors need the gather mode and all per-sample actor arrays");
+    a.ag = to_dev(actor_grids);
+    a.as = ActorSamplesDev{actor_samples->grid_id, actor_samples->pos, actor_samples->std, actor_samples->dirs};
+  }
   const int64_t tiles = (M + tc::kRows - 1) / tc::kRows;
   const unsigned nblk = static_cast<unsigned>(std::min<int64_t>((tiles + kFGroups - 1) / kFGroups, sm_count()));
   auto s = static_cast<cudaStream_t>(stream);
-#define NRB_FUSED_FWD(FF)                                                                                                      \
+#define NRB_FUSED_FWD(FF, AA)                                                                                                  \
   {                                                                                                                            \
-    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_fused_fwd_kernel<FF>), FusedFwdSmem::total); \
+    cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(field_fused_fwd_kernel<FF, AA>), FusedFwdSmem::total); \
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_field_fused_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));  \
-    field_fused_fwd_kernel<FF><<<nblk, kFThreads, FusedFwdSmem::total, s>>>(fused_params(p), gd, a);                           \
+    field_fused_fwd_kernel<FF, AA><<<nblk, kFThreads, FusedFwdSmem::total, s>>>(fused_params(p), gd, a);                       \
   }
-  if (F == 2) NRB_FUSED_FWD(2) else if (F == 4) NRB_FUSED_FWD(4) else NRB_FUSED_FWD(0)
+  if (F == 2 && actors) NRB_FUSED_FWD(2, true) else if (F == 4 && actors) NRB_FUSED_FWD(4, true)
+  else if (F == 2) NRB_FUSED_FWD(2, false) else if (F == 4) NRB_FUSED_FWD(4, false) else NRB_FUSED_FWD(0, false)
 #undef NRB_FUSED_FWD
   return finish_launch("nrb_field_fused_fwd");
 }
@@ -1064,6 +1104,9 @@ extern "C" int nrb_field_fused_bwd(const nrb_field_mlp_t* p, const nrb_field_fus
   a.sh = in->sh, a.sdf = in->sdf, a.alpha = in->alpha;
   a.dfeature = in->dfeature, a.dfeat_ray = in->dfeat_ray, a.weights = in->weights, a.dsdf = in->dsdf, a.dalpha = in->dalpha;
   a.samples_per_ray = samples_per_ray, a.M = M;
+  a.actor_grid_id = in->actor_grid_id, a.actor_dirs = in->actor_dirs;
+  NRB_REQUIRE((a.actor_grid_id == nullptr) == (a.actor_dirs == nullptr), NRB_ERR_BAD_ARG,
+              "nrb_field_fused_bwd: actor_grid_id and actor_dirs go together");
   a.dximg = reinterpret_cast<float4*>(out->dximg);
   for (int l = 0; l < 5; ++l) {
     a.dw[l] = out->dweights[l];
@@ -1083,7 +1126,8 @@ extern "C" int nrb_field_fused_bwd(const nrb_field_mlp_t* p, const nrb_field_fus
 }
 
 extern "C" int nrb_hash_bwd_image(const nrb_grid_t* grid, const float* x, const float* std, const float* dyimg,
-                                  float* dtable, int64_t M, void* workspace, int64_t workspace_bytes, nrb_stream_t stream) {
+                                  float* dtable, const int32_t* actor_grid_id, int64_t M, void* workspace,
+                                  int64_t workspace_bytes, nrb_stream_t stream) {
   if (int rc = check_grid(grid)) return rc;
   NRB_REQUIRE(x && dyimg && dtable && M >= 0, NRB_ERR_BAD_ARG, "nrb_hash_bwd_image: null pointer or negative M");
   NRB_REQUIRE(aligned16(dyimg) && aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_hash_bwd_image: dyimg/dtable must be 16-byte aligned");
@@ -1098,11 +1142,11 @@ extern "C" int nrb_hash_bwd_image(const nrb_grid_t* grid, const float* x, const 
   const unsigned nblk = blocks_for(M, 256);
   switch (grid->features_per_level) {
     case 2:
-      hash_bwd_img_kernel<2><<<nblk, 256, 0, s>>>(g, plan, x, std, dyimg, dtable, M);
+      hash_bwd_img_kernel<2><<<nblk, 256, 0, s>>>(g, plan, x, std, dyimg, dtable, actor_grid_id, M);
       launch_fold<2>(grid, plan, dtable, vertices, s);
       break;
     case 4:
-      hash_bwd_img_kernel<4><<<nblk, 256, 0, s>>>(g, plan, x, std, dyimg, dtable, M);
+      hash_bwd_img_kernel<4><<<nblk, 256, 0, s>>>(g, plan, x, std, dyimg, dtable, actor_grid_id, M);
       launch_fold<4>(grid, plan, dtable, vertices, s);
       break;
     default:

@@ -348,6 +348,36 @@ class NeuRADHashEncoding(nn.Module):
         dirs = rays.directions[:, None, :].expand(-1, iv.num_samples, -1)
         return self._apply_actors(feats, mean, wstd, dirs, times.reshape(-1))
 
+    ray_flip_override: Optional[Tensor] = None
+    """Tests: replay a recorded per-ray mirror draw ([N] of +1 / -1) instead of drawing one."""
+
+    def _draw_flip(self, n: int, device) -> Optional[Tensor]:
+        """-1 with probability flip_prob, per ray, in training (neurad_encoding.py:218-225)."""
+        if not (self.training and self.config.actor.flip_prob > 1.0e-7):
+            return None
+        if self.ray_flip_override is not None:
+            return self.ray_flip_override
+        return torch.bernoulli(torch.full((n,), self.config.actor.flip_prob, device=device)) * -2 + 1
+
+    def can_assign_in_kernel(self) -> bool:
+        """The actor kernels cover the reference's default actor grids (4 levels x 4 features, one table shape) for up to 32
+        actors, without gradients to the actor poses (those take the torch bookkeeping below)."""
+        if not self.has_actors or len(self.actor_grids) == 0 or len(self.actor_grids) > 32:
+            return False
+        a = self.config.actor
+        return a.num_levels == 4 and a.hashgrid_dim == 4 and not any(
+            p.requires_grad for p in getattr(self.actors, "parameters", lambda: [])()) 
+
+    @torch.no_grad()
+    def assign_actors(self, rays: F.RayData, iv: F.SampleIntervals, times: Tensor) -> "F.ActorBatch":
+        """Which samples fall into which actor box, in one kernel (csrc/actors.cu): no nonzero(), no host synchronisation."""
+        boxes2world, valid = self.actors.get_boxes2world(times.reshape(-1), flatten=False)
+        world2boxes = _pose_inverse(boxes2world)
+        flip = self._draw_flip(rays.num_rays, rays.origins.device)
+        grid_id, pos, std, dirs = F.actor_assign(rays, iv, world2boxes, valid, self.actors.actor_bounds(), self.actors.actor_to_id,
+                                                 flip, self.actor_scale)
+        return F.ActorBatch(grid_id, pos, std, dirs, [g.hash_table for g in self.actor_grids], self.actor_grids[0].spec)
+
     @torch.no_grad()
     def _actor_indices(self, mean: Tensor, boxes2world: Tensor, valid: Tensor, world2boxes: Tensor, bounds: Tensor):
         """(ray, sample, actor) of the samples inside actor boxes: ray line vs bounding sphere, sample vs sphere, then
@@ -389,8 +419,8 @@ class NeuRADHashEncoding(nn.Module):
                 d = _transform(dirs[ri, si], w2b, with_translation=False)
                 d = d / (torch.linalg.norm(d, dim=-1, keepdim=True) + 1.0e-7)
             if self.training and self.config.actor.flip_prob > 1.0e-7:
-                if ray_flip is None:  # -1 with probability flip_prob, per ray (neurad_encoding.py:218-225)
-                    ray_flip = torch.bernoulli(torch.full((n,), self.config.actor.flip_prob, device=mean.device)) * -2 + 1
+                if ray_flip is None:
+                    ray_flip = self._draw_flip(n, mean.device)
                 f = ray_flip.to(pos.dtype)[ri][:, None]
                 pos = torch.cat([pos[:, :1] * f, pos[:, 1:]], dim=-1)
                 if dirs is not None:

@@ -36,6 +36,16 @@ class FieldHeadNames(Enum):
     SDF = "sdf"
     ALPHA = "alpha"
 
+    # The reference model indexes a field's output dict with ITS enum (models/neuradar.py:1011): members of the two
+    # classes must be interchangeable as dictionary keys, so equality and hashing go by member name / value.
+    def __eq__(self, other):
+        if isinstance(other, Enum) and type(other).__name__ == "FieldHeadNames":
+            return self.value == other.value
+        return NotImplemented
+
+    def __hash__(self):
+        return hash(self._name_)
+
 
 def get_normalized_directions(directions: Tensor) -> Tensor:
     """(d + 1) / 2 (fields/base_field.py:136-142)."""
@@ -125,11 +135,14 @@ class NeuRADField(nn.Module):
         beta, beta_min = self.sdf_to_density.beta, self.sdf_to_density.beta_min_value
         grid = self.hashgrid.static_grid
         with_actors = self.hashgrid.has_actors and times is not None
-        if self.fused and not with_actors and grid.features_per_level in (2, 4):
-            # the 32 hash features are gathered inside the MLP kernel and never reach HBM
+        if self.fused and grid.features_per_level in (2, 4) and (not with_actors or self.hashgrid.can_assign_in_kernel()):
+            # the 32 hash features are gathered inside the MLP kernel and never reach HBM; samples inside an actor box
+            # (assigned by one kernel) read their actor's grid there
             x3, std = F.frustum_gaussians(rays, iv, self.hashgrid.static_scale)
             sh = self.direction_encoding(get_normalized_directions(rays.directions))
-            return F.field_fused(grid.hash_table, None, x3, std, sh, iv.num_samples, grid.spec, weights, biases, beta, beta_min)
+            actors = self.hashgrid.assign_actors(rays, iv, times) if with_actors else None
+            return F.field_fused(grid.hash_table, None, x3, std, sh, iv.num_samples, grid.spec, weights, biases, beta, beta_min,
+                                 actors)
         features, sample_dirs = self.hashgrid.encode_samples(rays, iv, times)
         if sample_dirs is None:  # directions are per ray: 16 SH values per ray, indexed by row / S in the kernel
             sh = self.direction_encoding(get_normalized_directions(rays.directions))
@@ -144,8 +157,8 @@ class NeuRADField(nn.Module):
     def can_render(self, ray_samples: RaySamples) -> bool:
         """True when `render` applies: default field shape, a 32-feature static grid and no dynamic actors."""
         grid = self.hashgrid.static_grid
-        return (self.fused and self._tensor_core_path() and not self.hashgrid.has_actors
-                and grid.features_per_level in (2, 4) and len(ray_samples.shape) == 2)
+        return (self.fused and self._tensor_core_path() and grid.features_per_level in (2, 4) and len(ray_samples.shape) == 2
+                and (not self.hashgrid.has_actors or (self.hashgrid.can_assign_in_kernel() and ray_samples.times is not None)))
 
     def render(self, ray_samples: RaySamples, trans_eps: float = 0.0):
         """Field + compositing tail in one autograd node (models/neuradar.py:500-517): returns (weights [N,S] after the
@@ -157,8 +170,11 @@ class NeuRADField(nn.Module):
         grid = self.hashgrid.static_grid
         x3, std = F.frustum_gaussians(rays, iv, self.hashgrid.static_scale)
         sh = self.direction_encoding(get_normalized_directions(rays.directions))
+        actors = None
+        if self.hashgrid.has_actors:
+            actors = self.hashgrid.assign_actors(rays, iv, ray_samples.times.reshape(rays.num_rays, -1)[:, 0])
         return F.field_render(grid.hash_table, x3, std, sh, iv, grid.spec, weights, biases, self.sdf_to_density.beta,
-                              self.sdf_to_density.beta_min_value, trans_eps)
+                              self.sdf_to_density.beta_min_value, trans_eps, actors)
 
     def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         N = rays.num_rays

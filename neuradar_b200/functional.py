@@ -459,6 +459,58 @@ def field_mlp(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Ten
 
 
 # ------------------------------------------------------------------------------------------------
+# dynamic actors: per-sample assignment (no compaction, no host synchronisation)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ActorBatch:
+    """Which samples of a [N,S] batch fall into which actor box (csrc/actors.cu): grid_id [M] int32 (-1 = static world),
+    pos [M,3] in the actor grid's unit cube, std [M], dirs [M,3] in the actor frame; plus the per-actor tables."""
+
+    grid_id: Tensor
+    pos: Tensor
+    std: Tensor
+    dirs: Tensor
+    tables: List[Tensor]
+    spec: GridSpec  # of ONE actor grid
+
+    def grids_struct(self, tables: Optional[Sequence[Tensor]] = None) -> "_lib.ActorGrids":
+        g = _lib.ActorGrids()
+        for i, t in enumerate(tables if tables is not None else self.tables):
+            g.tables[i] = ptr(t)
+        for i, sc in enumerate(self.spec.scalings):
+            g.scalings[i] = sc
+        g.num_levels, g.features_per_level = self.spec.num_levels, self.spec.features_per_level
+        g.log2_hashmap_size, g.num_grids = self.spec.log2_hashmap_size, len(self.tables)
+        return g
+
+    def samples_struct(self) -> "_lib.ActorSamples":
+        a = _lib.ActorSamples()
+        a.grid_id, a.pos, a.std, a.dirs = ptr(self.grid_id), ptr(self.pos), ptr(self.std), ptr(self.dirs)
+        return a
+
+
+def actor_assign(rays: RayData, iv: SampleIntervals, world2boxes: Tensor, valid: Tensor, bounds: Tensor, actor_to_id: Tensor,
+                 flip: Optional[Tensor], actor_scale: float) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+    """NeuRADHashEncoding._split_static_vs_actors as one kernel: (grid_id [M] int32, pos [M,3], std [M], dirs [M,3]) of the
+    M = N*S samples; world2boxes [N,A,3,4], valid [N,A], bounds [A,3], actor_to_id [A], flip [N] (+1 / -1) or None."""
+    N, S = rays.num_rays, iv.num_samples
+    dev = rays.origins.device
+    w2b = f32c(world2boxes.detach()[..., :3, :4])
+    A = w2b.shape[1]
+    val, bnd = _u8(valid), f32c(bounds.detach())
+    a2i = actor_to_id.to(device=dev, dtype=torch.int32).contiguous()
+    flp = None if flip is None else f32c(flip.reshape(-1))
+    grid_id = torch.empty((N * S,), device=dev, dtype=torch.int32)
+    pos = torch.zeros((N * S, 3), device=dev, dtype=torch.float32)
+    std = torch.zeros((N * S,), device=dev, dtype=torch.float32)
+    dirs = torch.zeros((N * S, 3), device=dev, dtype=torch.float32)
+    r, i = rays.struct(), iv.struct()
+    _lib.call("nrb_actor_assign", C.byref(r), C.byref(i), ptr(w2b), ptr(val), ptr(bnd), ptr(a2i), A, ptr(flp), float(actor_scale),
+              ptr(grid_id), ptr(pos), ptr(std), ptr(dirs), None, stream_ptr())
+    return grid_id, pos, std, dirs
+
+
+# ------------------------------------------------------------------------------------------------
 # fused field: hash gather + both MLPs in one kernel; backward recomputes the activations
 # ------------------------------------------------------------------------------------------------
 def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf, dalpha):
@@ -468,6 +520,9 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
     weights_ = list(saved_tensors[9:14])
     rest = list(saved_tensors[14:])
     biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
+    actors = None
+    if ctx.actor_spec is not None:  # [grid_id, pos, std, dirs, *tables] ride at the end
+        actors = ActorBatch(rest[0], rest[1], rest[2], rest[3], list(rest[4:]), ctx.actor_spec)
     M, dev = sdf.shape[0], sdf.device
     need_dx = ctx.gather or ctx.needs_x_grad
     dximg = torch.empty((int(_lib_().nrb_field_fused_image_bytes(M)) // 4,), device=dev, dtype=torch.float32) if need_dx else None
@@ -492,6 +547,8 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
     bi.sh, bi.sdf, bi.alpha = ptr(sh), ptr(sdf), ptr(alpha)
     bi.dfeature, bi.dfeat_ray, bi.weights = ptr(dfeature), ptr(dfeat_ray), ptr(weights)
     bi.dsdf, bi.dalpha = ptr(dsdf), ptr(dalpha)
+    if actors is not None:
+        bi.actor_grid_id, bi.actor_dirs = ptr(actors.grid_id), ptr(actors.dirs)
     bo = _lib.FieldFusedBwdOut()
     bo.dximg = ptr(dximg)
     for i in range(5):
@@ -505,25 +562,38 @@ def _field_fused_backward(ctx, saved_tensors, dfeature, dfeat_ray, weights, dsdf
         dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
         g = spec.struct(table)
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), M)), dev)
-        _lib.call("nrb_hash_bwd_image", C.byref(g), ptr(x3), ptr(std), ptr(dximg), ptr(dtable), M, ws, ws_bytes, stream_ptr(),
-                  tag="nrb_hash_bwd:" + spec.tag)
+        _lib.call("nrb_hash_bwd_image", C.byref(g), ptr(x3), ptr(std), ptr(dximg), ptr(dtable),
+                  None if actors is None else ptr(actors.grid_id), M, ws, ws_bytes, stream_ptr(), tag="nrb_hash_bwd:" + spec.tag)
         if ctx.sink is not None:
             _sink_written(table)
             dtable = None
     elif ctx.needs_x_grad:
         dx = dximg.view(-1, 8, 128, 4).permute(0, 2, 1, 3).reshape(-1, 32)[:M]
+    dactor = []
+    if actors is not None:  # the actor samples' gradient goes to their own tables
+        dactor = [sk if sk is not None else torch.zeros_like(t) for t, sk in zip(actors.tables, ctx.actor_sinks)]
+        arr = (C.c_void_p * len(dactor))(*[ptr(t) for t in dactor])
+        ag, asmp = actors.grids_struct(), actors.samples_struct()
+        _lib.call("nrb_actor_scatter", C.byref(ag), arr, C.byref(asmp), ptr(dximg), None, M, stream_ptr())
+        dactor = [None if sk is not None else t for t, sk in zip(dactor, ctx.actor_sinks)]
+    ctx.dactor = dactor
     if any(sk is not None for sk in psinks):
         _sink_written(next(t for t, sk in zip(tensors, psinks) if sk is not None))
     ret = [None if sk is not None else gr for gr, sk in zip(grads, psinks)]
     return dx, dtable, ret[0], ret[1:6], ret[6:11]
 
 
-def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, param_sinks=None):
+def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, param_sinks=None,
+                         actors: Optional[ActorBatch] = None):
     """Launch nrb_field_fused_fwd and stash what the backward needs on ctx.  Returns (feature, sdf, alpha)."""
     gather = table is not None
     sh, beta = f32c(sh.detach()), f32c(beta)
     weights = [f32c(w) for w in params[:5]]
-    biases = [None if b is None else f32c(b) for b in params[5:]]
+    biases = [None if b is None else f32c(b) for b in params[5:10]]
+    ag = asmp = None
+    if actors is not None:
+        actors = ActorBatch(actors.grid_id, actors.pos, actors.std, actors.dirs, [f32c(t) for t in params[10:]], actors.spec)
+        ag, asmp = actors.grids_struct(), actors.samples_struct()
     if gather:
         table, x3 = f32c(table), f32c(x3)
         std = None if std is None else f32c(std.reshape(-1))
@@ -544,10 +614,15 @@ def _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, 
     m = _field_struct(weights, biases, beta, beta_min)
     _lib.call("nrb_field_fused_fwd", C.byref(m), C.byref(g) if gather else None, ptr(x3) if gather else None,
               ptr(std) if gather else None, None if gather else ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature),
-              ptr(sdf), ptr(alpha), C.byref(sv), stream_ptr())
+              ptr(sdf), ptr(alpha), C.byref(sv), None if ag is None else C.byref(ag), None if asmp is None else C.byref(asmp),
+              stream_ptr())
+    ctx.actor_spec = None
     if train:
+        extra = [] if actors is None else [actors.grid_id, actors.pos, actors.std, actors.dirs, *actors.tables]
+        ctx.actor_spec = None if actors is None else actors.spec
+        ctx.actor_sinks = [] if actors is None else [grad_sink_of(t) for t in params[10:]]
         ctx.save_for_backward(table if gather else None, x3 if gather else None, std if gather else None, ximg, masks, sh,
-                              beta, sdf, alpha, *weights, *[b for b in biases if b is not None])
+                              beta, sdf, alpha, *weights, *[b for b in biases if b is not None], *extra)
         ctx.has_bias = [b is not None for b in biases]
         ctx.samples_per_ray, ctx.beta_min, ctx.gather, ctx.spec = int(samples_per_ray), float(beta_min), gather, spec
         ctx.param_sinks = param_sinks if param_sinks is not None else [None] * 11
@@ -560,12 +635,13 @@ class _FieldFused(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, table, x, x3, std, sh, samples_per_ray: int, beta_min: float, spec, beta, *params):
+    def forward(ctx, table, x, x3, std, sh, samples_per_ray: int, beta_min: float, spec, actors, beta, *params):
         ctx.sink = grad_sink_of(table) if table is not None else None
         train = any(ctx.needs_input_grad)
         ctx.needs_x_grad = x is not None and ctx.needs_input_grad[1]
-        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params]
-        return _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, sinks)
+        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params[:10]]
+        return _field_fused_forward(ctx, table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, params, train, sinks,
+                                    actors)
 
     @staticmethod
     @custom_bwd(device_type="cuda")
@@ -576,14 +652,17 @@ class _FieldFused(torch.autograd.Function):
         dsdf = None if dsdf is None else f32c(dsdf)
         dalpha = None if dalpha is None else f32c(dalpha)
         dx, dtable, dbeta, dws, dbs = _field_fused_backward(ctx, ctx.saved_tensors, dfeature, None, None, dsdf, dalpha)
-        return (dtable, dx, None, None, None, None, None, None, dbeta, *dws, *dbs)
+        return (dtable, dx, None, None, None, None, None, None, None, dbeta, *dws, *dbs, *ctx.dactor)
 
 
 def field_fused(table: Optional[Tensor], x: Optional[Tensor], x3: Optional[Tensor], std: Optional[Tensor], sh: Tensor,
                 samples_per_ray: int, spec: Optional[GridSpec], weights: Sequence[Tensor],
-                biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """Fused field.  Gather mode: `table` + sample means `x3` [M,3] + `std` [M]; otherwise hash features `x` [M,32]."""
-    return _FieldFused.apply(table, x, x3, std, sh, samples_per_ray, beta_min, spec, beta, *weights, *biases)
+                biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float,
+                actors: Optional[ActorBatch] = None) -> Tuple[Tensor, Tensor, Tensor]:
+    """Fused field.  Gather mode: `table` + sample means `x3` [M,3] + `std` [M] (+ `actors`: the samples inside actor boxes
+    read their actor's grid instead); otherwise hash features `x` [M,32]."""
+    extra = [] if actors is None else list(actors.tables)
+    return _FieldFused.apply(table, x, x3, std, sh, samples_per_ray, beta_min, spec, actors, beta, *weights, *biases, *extra)
 
 
 class _FieldRender(torch.autograd.Function):
@@ -594,13 +673,14 @@ class _FieldRender(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, table, x3, std, sh, iv: "SampleIntervals", beta_min: float, spec, trans_eps: float, beta, *params):
+    def forward(ctx, table, x3, std, sh, iv: "SampleIntervals", beta_min: float, spec, trans_eps: float, actors, beta, *params):
         ctx.sink = grad_sink_of(table)
         train = any(ctx.needs_input_grad)
         ctx.needs_x_grad = False
-        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params]
+        sinks = [grad_sink_of(beta)] + [grad_sink_of(q) for q in params[:10]]
         S = iv.num_samples
-        feature, sdf, alpha = _field_fused_forward(ctx, table, None, x3, std, sh, S, beta_min, spec, beta, params, train, sinks)
+        feature, sdf, alpha = _field_fused_forward(ctx, table, None, x3, std, sh, S, beta_min, spec, beta, params, train, sinks,
+                                                   actors)
         N, dev = alpha.shape[0] // S, alpha.device
         weights = torch.empty((N, S), device=dev, dtype=torch.float32)
         features = torch.empty((N, 32), device=dev, dtype=torch.float32)
@@ -630,14 +710,15 @@ class _FieldRender(torch.autograd.Function):
                   ptr(ddepth), ptr(dacc), ptr(dalphas), None, stream_ptr())
         _, dtable, dbeta, dws, dbs = _field_fused_backward(ctx, ctx.saved_tensors, None, dfeatures, weights.reshape(-1), None,
                                                            dalphas)
-        return (dtable, None, None, None, None, None, None, None, dbeta, *dws, *dbs)
+        return (dtable, None, None, None, None, None, None, None, None, dbeta, *dws, *dbs, *ctx.dactor)
 
 
 def field_render(table: Tensor, x3: Tensor, std: Optional[Tensor], sh: Tensor, iv: SampleIntervals, spec: GridSpec,
                  weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float,
-                 trans_eps: float = 0.0) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
+                 trans_eps: float = 0.0, actors: Optional[ActorBatch] = None) -> Tuple[Tensor, Tensor, Tensor, Tensor]:
     """(weights [N,S], features [N,32], depth [N], accumulation [N]) of the rays whose samples are (x3, std, iv)."""
-    return _FieldRender.apply(table, x3, std, sh, iv, beta_min, spec, trans_eps, beta, *weights, *biases)
+    extra = [] if actors is None else list(actors.tables)
+    return _FieldRender.apply(table, x3, std, sh, iv, beta_min, spec, trans_eps, actors, beta, *weights, *biases, *extra)
 
 
 def sh16(directions: Tensor, normalize_to_unit_cube: bool = False) -> Tensor:

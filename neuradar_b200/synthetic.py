@@ -137,6 +137,7 @@ class SyntheticActors(torch.nn.Module):
         self.register_buffer("yaw_rate", ((torch.rand((n_actors,), generator=g) - 0.5) * 0.02).to(device))
         self.register_buffer("bounds", torch.tensor([1.0, 2.3, 0.85]).repeat(n_actors, 1).to(device))
         self.register_buffer("actor_to_id", torch.arange(n_actors).to(device))
+        self.register_buffer("bottom_row", torch.tensor([0.0, 0.0, 0.0, 1.0]).to(device))
 
     def actor_bounds(self) -> Tensor:
         return self.bounds
@@ -149,7 +150,7 @@ class SyntheticActors(torch.nn.Module):
         z, o = torch.zeros_like(c), torch.ones_like(c)
         rot = torch.stack([torch.stack([c, -s, z], -1), torch.stack([s, c, z], -1), torch.stack([z, z, o], -1)], -2)
         top = torch.cat([rot, pos[..., None]], -1)                                 # [N, A, 3, 4]
-        bottom = torch.tensor([0.0, 0.0, 0.0, 1.0], device=t.device).expand(*top.shape[:2], 1, 4)
+        bottom = self.bottom_row.expand(*top.shape[:2], 1, 4)
         b2w = torch.cat([top, bottom], -2)
         valid = torch.ones(b2w.shape[:2], dtype=torch.bool, device=t.device)
         if flatten:

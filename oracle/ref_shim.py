@@ -68,7 +68,47 @@ def install() -> str:
         sys.modules[name] = mod
     import typing
 
+    _install_nerfacc_dense(sys.modules["nerfacc"])
     sys.modules["git"].Optional = typing.Optional  # model_components/radar_utils.py:20 imports typing.Optional through GitPython
     if root not in sys.path:
         sys.path.insert(0, root)
     return root
+
+
+def _install_nerfacc_dense(mod) -> None:
+    """Give the `nerfacc` placeholder the three entry points the model calls (nerfacc==0.5.2 is a third-party package that
+    is not vendored).  CPU tensors: the dense contract restated in torch - weights = alpha *
+    exclusive_cumprod(1 - alpha), accumulate = sum_s w v - which is what makes the reference model a CPU oracle for the
+    compositing tail; CUDA tensors: the product's drop-in module (neuradar_b200.nerfacc_compat), i.e. what a box without
+    nerfacc would run."""
+    import torch
+
+    def _gpu():
+        from neuradar_b200 import nerfacc_compat
+
+        return nerfacc_compat
+
+    def render_weight_from_alpha(alphas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+        if alphas.is_cuda:
+            return _gpu().render_weight_from_alpha(alphas, packed_info, ray_indices, n_rays, prefix_trans)
+        trans = torch.cumprod(torch.cat([torch.ones_like(alphas[..., :1]), 1 - alphas[..., :-1]], dim=-1), dim=-1)
+        return alphas * trans, trans
+
+    def render_weight_from_density(t_starts, t_ends, sigmas, packed_info=None, ray_indices=None, n_rays=None, prefix_trans=None):
+        if sigmas.is_cuda:
+            return _gpu().render_weight_from_density(t_starts, t_ends, sigmas, packed_info, ray_indices, n_rays, prefix_trans)
+        ds = sigmas * (t_ends - t_starts)
+        alphas = 1 - torch.exp(-ds)
+        trans = torch.exp(-torch.cat([torch.zeros_like(ds[..., :1]), torch.cumsum(ds[..., :-1], dim=-1)], dim=-1))
+        return alphas * trans, trans, alphas
+
+    def accumulate_along_rays(weights, values=None, ray_indices=None, n_rays=None):
+        if weights.is_cuda:
+            return _gpu().accumulate_along_rays(weights, values, ray_indices, n_rays)
+        if values is None:
+            return weights.sum(dim=-1, keepdim=True)
+        return (weights[..., None] * values).sum(dim=-2)
+
+    mod.render_weight_from_alpha = render_weight_from_alpha
+    mod.render_weight_from_density = render_weight_from_density
+    mod.accumulate_along_rays = accumulate_along_rays

@@ -617,8 +617,8 @@ def test_dynamic_actor_branch_golden(nb, golden, mode):
     rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
     if mode == "train":  # replay the reference's per-ray flip draw
         flip = g["train_ray_flip"].to(DEV)
-        orig = fld.hashgrid._apply_actors
-        fld.hashgrid._apply_actors = lambda *a, **k: orig(*a, ray_flip=flip, **k)
+        fld.hashgrid.ray_flip_override = flip
+    assert fld.hashgrid.can_assign_in_kernel()  # the actor kernels (csrc/actors.cu), not the torch bookkeeping
     out = fld(rs)
     ref_inside = (g[f"{mode}_grid_features"][:, 16:] == 0).all(dim=-1)
     assert int(ref_inside.sum()) > 100
@@ -626,8 +626,6 @@ def test_dynamic_actor_branch_golden(nb, golden, mode):
     assert float((out[nb.FieldHeadNames.ALPHA].detach().cpu() - g[f"{mode}_alpha"]).abs().max()) <= 1e-3
     # the grid stage alone, through the reference-shaped API (GaussiansStd in, features + directions out)
     gs = rs.frustums.get_fast_isotropic_gaussian(1)
-    if mode == "train":
-        fld.hashgrid._apply_actors = lambda *a, **k: orig(*a, ray_flip=flip, **k)
     feats, dirs = fld.hashgrid(gs, rs.times, rs.frustums.directions)
     assert torch.equal((feats[:, 16:] == 0).all(dim=-1).cpu(), ref_inside), "the same samples must be claimed by actors"
     assert rel_err(feats, g[f"{mode}_grid_features"]) <= 1e-4
@@ -642,3 +640,50 @@ def test_dynamic_actor_branch_golden(nb, golden, mode):
             if float(ref.abs().max()) > 0:
                 assert rel_err(got, ref) <= 1e-3, i
         assert rel_err(fld.mlp_geo.layers[0].weight.grad, g["train_d_geo_w0"]) <= 1e-3
+
+
+def test_actor_path_has_no_host_sync(nb):
+    """The field forward + backward in a scene with dynamic actors (config-4 shape, 16 actors) must not synchronise the
+    host: the reference's three nonzero() round trips and its python loop over actors are one kernel here."""
+    import neuradar_b200 as pkg
+    from neuradar_b200.synthetic import SyntheticActors, synthetic_rays
+
+    n, S = 512, 64
+    actors = SyntheticActors(16, device=DEV)
+    cfg = pkg.NeuRADFieldConfig(grid=pkg.NeuRADHashEncodingConfig(
+        static=pkg.StaticSettings(hashgrid_dim=4, num_levels=8, base_res=32, max_res=8192, log2_hashmap_size=14),
+        actor=pkg.ActorSettings(flip_prob=0.25, log2_hashmap_size=10)))
+    fld = pkg.NeuRADField(cfg, actors=actors, static_scale=100.0).to(DEV)
+    fld.train()
+    with torch.no_grad():
+        fld.hashgrid.static_grid.hash_table.mul_(300.0)
+        for g in fld.hashgrid.actor_grids:
+            g.hash_table.mul_(300.0)
+    r = synthetic_rays(n, seed=2)
+    # aim a third of the rays at actor boxes so that they are certainly hit
+    centres = actors.centres[torch.arange(n // 3) % 16].cpu()
+    d = centres - r["origins"][: n // 3]
+    r["directions"][: n // 3] = d / d.norm(dim=-1, keepdim=True)
+    rb = nb.RayBundle(origins=r["origins"].to(DEV), directions=r["directions"].to(DEV), pixel_area=r["pixel_area"].to(DEV),
+                      times=r["times"].to(DEV), metadata={})
+    bins = (torch.linspace(0.5, 60.0, S + 1)[None, :].repeat(n, 1)).to(DEV)
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    out = fld(rs)  # warm-up (allocations, caches)
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        out = fld(rs)
+        (out[nb.FieldHeadNames.FEATURE].sum() + out[nb.FieldHeadNames.ALPHA].sum()).backward()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    rays, iv = rs.per_ray()
+    batch = fld.hashgrid.assign_actors(rays, iv, rs.times.reshape(n, -1)[:, 0])
+    inside = int((batch.grid_id >= 0).sum())
+    assert inside > 50, inside
+    assert sum(float(g.hash_table.grad.abs().sum()) > 0 for g in fld.hashgrid.actor_grids) >= 4
+    # against the torch bookkeeping of the same module (the reference's algorithm, round 1) on the same samples
+    fld.eval()
+    feats_kernel = fld(rs)[nb.FieldHeadNames.FEATURE]
+    fld.fused = False
+    feats_torch = fld(rs)[nb.FieldHeadNames.FEATURE]
+    assert rel_err(feats_kernel, feats_torch) <= 1e-5
