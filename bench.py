@@ -383,8 +383,7 @@ def run_b200(args, rank, world, local_rank):
     torch.cuda.current_stream(dev).wait_stream(side)
     torch.cuda.synchronize()
     graph, graph_note, launches_per_step = None, "eager launches (--no-graph)", None
-    has_actors = w.actors > 0
-    if not args.no_graph and not has_actors:
+    if not args.no_graph:
         try:
             l0 = _lib.launch_count()
             graph = torch.cuda.CUDAGraph()
@@ -401,8 +400,6 @@ def run_b200(args, rank, world, local_rank):
             if world == 1:
                 os.execv(sys.executable, [sys.executable] + sys.argv + ["--no-graph"])
             raise
-    elif has_actors:
-        graph_note = "eager launches (the dynamic-actor bookkeeping sizes tensors on the host)"
 
     def run_step():
         if graph is not None:

@@ -378,16 +378,19 @@ int nrb_grad_check(const float* g, int64_t n, float* found_inf, nrb_stream_t str
  * (fields/neurad_field.py:208-213, cameras/rays.py:188-210) in one kernel, one warp per ray:
  * gaussians -> contraction -> hash encode -> level weights -> Linear(L*F, 1, bias=False) -> trunc_exp -> weights.
  * decoder_w [L*F].  Outputs: density [N,S], weights [N,S]; when `saved_feats` [N,S,L*F] and `saved_pre` [N,S]
- * are non-NULL the rescaled features and the pre-activation are kept for the backward pass. */
+ * are non-NULL the rescaled features and the pre-activation are kept for the backward pass.  Dynamic actors (optional,
+ * both NULL otherwise): samples with actor_samples->grid_id >= 0 read the 4-level grid of their actor (same features per
+ * level as the static grid; features beyond the actor grid's are zero), see nrb_actor_assign. */
 int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w, float static_scale,
                      const nrb_intervals_t* iv, float* density, float* weights, float* saved_feats, float* saved_pre,
-                     nrb_stream_t stream);
+                     const nrb_actor_grids_t* actor_grids, const nrb_actor_samples_t* actor_samples, nrb_stream_t stream);
 /* Backward of the fused round given dweights [N,S] and/or ddensity [N,S] (either may be NULL):
  * dtable += ..., ddecoder_w [L*F] += ...; workspace as for nrb_hash_bwd (nrb_hash_bwd_workspace_bytes(grid, N*S)). */
 int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w, float static_scale,
                      const nrb_intervals_t* iv, const float* saved_feats, const float* saved_pre,
                      const float* dweights, const float* ddensity, float* dtable, float* ddecoder_w,
-                     void* workspace, int64_t workspace_bytes, nrb_stream_t stream);
+                     void* workspace, int64_t workspace_bytes, const nrb_actor_grids_t* actor_grids,
+                     const nrb_actor_samples_t* actor_samples, float* const* actor_dtables, nrb_stream_t stream);
 
 #ifdef __cplusplus
 }

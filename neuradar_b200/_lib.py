@@ -174,8 +174,10 @@ SIGNATURES = {
     "nrb_grad_check": [_P, _I64, _P, _P],
     "nrb_distortion_loss": [_P, _I64, _P, _I64, _I32, _P, _P, _P],
     "nrb_interlevel_loss": [_P, _I64, _P, _I32, _P, _I64, _P, _I32, _F, _I64, _P, _P, _P],
-    "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P],
-    "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P, _I64, _P],
+    "nrb_proposal_fwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P,
+                         C.POINTER(ActorGrids), C.POINTER(ActorSamples), _P],
+    "nrb_proposal_bwd": [C.POINTER(Rays), C.POINTER(Grid), _P, _F, C.POINTER(Intervals), _P, _P, _P, _P, _P, _P, _P, _I64,
+                         C.POINTER(ActorGrids), C.POINTER(ActorSamples), C.POINTER(C.c_void_p), _P],
 }
 _RESTYPES = {"nrb_last_error_string": C.c_char_p, "nrb_launch_count": C.c_int64, "nrb_hash_bwd_workspace_bytes": C.c_int64, "nrb_field_saved_ld": C.c_int64,
              "nrb_field_fused_image_bytes": C.c_int64}

@@ -3,6 +3,7 @@
 // Semantics: NeuRADProposalField.get_density (nerfstudio/fields/neurad_field.py:208-213) followed by
 // RaySamples.get_weights (nerfstudio/cameras/rays.py:188-210); trunc_exp backward clamps the exponent to +-15
 // (nerfstudio/field_components/activations.py:28-41).
+#include "actor_grid.cuh"
 #include "common.cuh"
 #include "hash_bwd_plan.cuh"
 
@@ -17,6 +18,13 @@ struct PropGrid {
   const float* decoder;  // [L*F] device pointer (density_decoder.weight)
   int num_levels;
   int log2_size;
+  // dynamic actors (optional): samples with agid >= 0 read the 4-level grid of their actor instead, features beyond
+  // 4 * F are zero (neurad_encoding.py:181-187); apos / astd come from nrb_actor_assign
+  const int32_t* agid;
+  const float* apos;
+  const float* astd;
+  ActorGridsDev ag;
+  float* adtables[NRB_MAX_ACTORS];  // backward: gradient tables of the actor grids
 };
 
 template <int F, bool kSave>
@@ -48,17 +56,42 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_fwd_kernel(
       const float start = st[i], end = en[i];
       const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, start, end, scale);
       float pre = 0.0f;
-      for (int l = 0; l < g.num_levels; ++l) {
-        const float scal = g.scalings[l];
-        const Cell c = locate_cell(q.x, q.y, q.z, scal, mask);
-        float v[F];
-        interpolate<F>(g.table + (static_cast<size_t>(l) << g.log2_size) * F, c, v);
-        const float lw = level_weight(scal, q.std);
+      const int agid = g.agid != nullptr ? g.agid[n * S + i] : -1;
+      if (agid >= 0) {  // inside an actor box: that actor's grid, zero-padded
+        const float ax = g.apos[3 * (n * S + i)], ay = g.apos[3 * (n * S + i) + 1], az = g.apos[3 * (n * S + i) + 2];
+        const float asd = g.astd[n * S + i];
+        const uint32_t amask = (1u << g.ag.log2_size) - 1u;
+        for (int l = 0; l < g.num_levels; ++l) {
+          float v[F];
 #pragma unroll
-        for (int j = 0; j < F; ++j) {
-          const float f = v[j] * lw;
-          pre = fmaf(f, s_dec[l * F + j], pre);
-          if constexpr (kSave) saved_feats[(n * S + i) * LF + l * F + j] = f;
+          for (int j = 0; j < F; ++j) v[j] = 0.0f;
+          float lw = 0.0f;
+          if (l < kActorLevels) {
+            const float scal = g.ag.scalings[l];
+            const Cell c = locate_cell(ax, ay, az, scal, amask);
+            interpolate<F>(g.ag.tables[agid] + (static_cast<size_t>(l) << g.ag.log2_size) * F, c, v);
+            lw = level_weight(scal, asd);
+          }
+#pragma unroll
+          for (int j = 0; j < F; ++j) {
+            const float f = v[j] * lw;
+            pre = fmaf(f, s_dec[l * F + j], pre);
+            if constexpr (kSave) saved_feats[(n * S + i) * LF + l * F + j] = f;
+          }
+        }
+      } else {
+        for (int l = 0; l < g.num_levels; ++l) {
+          const float scal = g.scalings[l];
+          const Cell c = locate_cell(q.x, q.y, q.z, scal, mask);
+          float v[F];
+          interpolate<F>(g.table + (static_cast<size_t>(l) << g.log2_size) * F, c, v);
+          const float lw = level_weight(scal, q.std);
+#pragma unroll
+          for (int j = 0; j < F; ++j) {
+            const float f = v[j] * lw;
+            pre = fmaf(f, s_dec[l * F + j], pre);
+            if constexpr (kSave) saved_feats[(n * S + i) * LF + l * F + j] = f;
+          }
         }
       }
       dens = expf(pre);
@@ -158,6 +191,27 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
         const float gpre = act ? gdens[c] * expf(fminf(fmaxf(pre[c], -15.0f), 15.0f)) : 0.0f;
         const Gaussian q = sample_gaussian(ox, oy, oz, dx, dy, dz, pa, st[ic], en[ic], scale);
         const float* sf = saved_feats + (n * S + ic) * LF;
+        const int agid = g.agid != nullptr ? g.agid[n * S + ic] : -1;
+        if (act && agid >= 0) {  // the sample's gradient goes to its actor's table (plain reductions: ~10 % of the samples)
+          const float ax = g.apos[3 * (n * S + ic)], ay = g.apos[3 * (n * S + ic) + 1], az = g.apos[3 * (n * S + ic) + 2];
+          const float asd = g.astd[n * S + ic];
+          const uint32_t amask = (1u << g.ag.log2_size) - 1u;
+#pragma unroll
+          for (int l = 0; l < kActorLevels; ++l) {
+            const float scal = g.ag.scalings[l];
+            const Cell cell = locate_cell(ax, ay, az, scal, amask);
+            const float lw = level_weight(scal, asd);
+            float gr[F];
+#pragma unroll
+            for (int j = 0; j < F; ++j) gr[j] = gpre * s_dec[l * F + j] * lw;
+            float w8[8];
+            corner_weights(cell, w8);
+            float* dt = g.adtables[agid] + (static_cast<size_t>(l) << g.ag.log2_size) * F;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) scatter_row<F>(dt, cell.row[k], gr, w8[k]);
+          }
+        }
+        const bool act_static = act && agid < 0;
 #pragma unroll
         for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
           if (l < g.num_levels) {
@@ -178,8 +232,8 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
               for (int k = 0; k < 8; ++k)
 #pragma unroll
                 for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
-              merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act, lane, dtable, spread);
-            } else if (act) {
+              merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act_static, lane, dtable, spread);
+            } else if (act_static) {
               scatter_corners<F>(plan, l, g.log2_size, scal, q.x, q.y, q.z, cell, gr, w8, dtable, spread);
             }
           }
@@ -198,8 +252,14 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
   if (threadIdx.x < LF && ddecoder != nullptr) atomicAdd(ddecoder + threadIdx.x, s_ddec[threadIdx.x]);
 }
 
-static PropGrid make_prop_grid(const nrb_grid_t* grid, const float* decoder) {
-  PropGrid out;
+static PropGrid make_prop_grid(const nrb_grid_t* grid, const float* decoder, const nrb_actor_grids_t* agrids = nullptr,
+                               const nrb_actor_samples_t* asamples = nullptr, float* const* adtables = nullptr) {
+  PropGrid out{};
+  if (agrids != nullptr) {
+    out.ag = to_dev(agrids);
+    out.agid = asamples->grid_id, out.apos = asamples->pos, out.astd = asamples->std;
+    for (int i = 0; i < agrids->num_grids; ++i) out.adtables[i] = adtables != nullptr ? adtables[i] : nullptr;
+  }
   out.table = grid->table;
   for (int i = 0; i < NRB_MAX_LEVELS; ++i) out.scalings[i] = grid->scalings[i];
   out.decoder = decoder;
@@ -222,16 +282,29 @@ static int check_proposal(const char* who, const nrb_rays_t* rays, const nrb_gri
 
 using namespace nrb;
 
+static int check_prop_actors(const char* who, const nrb_grid_t* grid, const nrb_actor_grids_t* agrids,
+                             const nrb_actor_samples_t* asamples) {
+  if (agrids == nullptr) return NRB_OK;
+  NRB_REQUIRE(agrids->num_grids >= 1 && agrids->num_grids <= NRB_MAX_ACTORS && agrids->num_levels == kActorLevels &&
+                  agrids->features_per_level == grid->features_per_level && grid->num_levels >= kActorLevels,
+              NRB_ERR_UNSUPPORTED, "%s: actor grids must have 4 levels and the static grid's features per level", who);
+  NRB_REQUIRE(asamples && asamples->grid_id && asamples->pos && asamples->std, NRB_ERR_BAD_ARG, "%s: actor samples missing", who);
+  for (int i = 0; i < agrids->num_grids; ++i) NRB_REQUIRE(agrids->tables[i] != nullptr, NRB_ERR_BAD_ARG, "%s: actor table %d", who, i);
+  return NRB_OK;
+}
+
 extern "C" int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
                                 float static_scale, const nrb_intervals_t* iv, float* density, float* weights,
-                                float* saved_feats, float* saved_pre, nrb_stream_t stream) {
+                                float* saved_feats, float* saved_pre, const nrb_actor_grids_t* actor_grids,
+                                const nrb_actor_samples_t* actor_samples, nrb_stream_t stream) {
   if (int rc = check_proposal("nrb_proposal_fwd", rays, grid, decoder_w, static_scale, iv)) return rc;
+  if (int rc = check_prop_actors("nrb_proposal_fwd", grid, actor_grids, actor_samples)) return rc;
   NRB_REQUIRE(weights != nullptr, NRB_ERR_BAD_ARG, "nrb_proposal_fwd: weights is null");
   NRB_REQUIRE((saved_feats == nullptr) == (saved_pre == nullptr), NRB_ERR_BAD_ARG,
               "nrb_proposal_fwd: saved_feats and saved_pre must be given together");
   const int64_t N = rays->num_rays;
   if (N == 0) return NRB_OK;
-  const PropGrid g = make_prop_grid(grid, decoder_w);
+  const PropGrid g = make_prop_grid(grid, decoder_w, actor_grids, actor_samples);
   const unsigned blocks = blocks_for(N, kPropWarps);
   auto s = static_cast<cudaStream_t>(stream);
   const bool save = saved_feats != nullptr;
@@ -251,14 +324,18 @@ extern "C" int nrb_proposal_fwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
 extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, const float* decoder_w,
                                 float static_scale, const nrb_intervals_t* iv, const float* saved_feats,
                                 const float* saved_pre, const float* dweights, const float* ddensity, float* dtable,
-                                float* ddecoder_w, void* workspace, int64_t workspace_bytes, nrb_stream_t stream) {
+                                float* ddecoder_w, void* workspace, int64_t workspace_bytes,
+                                const nrb_actor_grids_t* actor_grids, const nrb_actor_samples_t* actor_samples,
+                                float* const* actor_dtables, nrb_stream_t stream) {
   if (int rc = check_proposal("nrb_proposal_bwd", rays, grid, decoder_w, static_scale, iv)) return rc;
+  if (int rc = check_prop_actors("nrb_proposal_bwd", grid, actor_grids, actor_samples)) return rc;
+  NRB_REQUIRE(actor_grids == nullptr || actor_dtables != nullptr, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: actor gradient tables missing");
   NRB_REQUIRE(saved_feats && saved_pre && dtable, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: null pointer");
   NRB_REQUIRE(dweights || ddensity, NRB_ERR_BAD_ARG, "nrb_proposal_bwd: no upstream gradient");
   NRB_REQUIRE(aligned16(dtable), NRB_ERR_ALIGNMENT, "nrb_proposal_bwd: dtable must be 16-byte aligned");
   const int64_t N = rays->num_rays;
   if (N == 0) return NRB_OK;
-  const PropGrid g = make_prop_grid(grid, decoder_w);
+  const PropGrid g = make_prop_grid(grid, decoder_w, actor_grids, actor_samples, actor_dtables);
   const unsigned blocks = blocks_for(N, kPropWarps);
   auto s = static_cast<cudaStream_t>(stream);
   BwdPlan plan;

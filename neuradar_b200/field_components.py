@@ -359,14 +359,18 @@ class NeuRADHashEncoding(nn.Module):
             return self.ray_flip_override
         return torch.bernoulli(torch.full((n,), self.config.actor.flip_prob, device=device)) * -2 + 1
 
-    def can_assign_in_kernel(self) -> bool:
-        """The actor kernels cover the reference's default actor grids (4 levels x 4 features, one table shape) for up to 32
-        actors, without gradients to the actor poses (those take the torch bookkeeping below)."""
+    def can_assign_in_kernel(self, proposal: bool = False) -> bool:
+        """The actor kernels cover the reference's default actor grids (4 levels, one table shape; 4 features in the field,
+        the static grid's feature count in a proposal network) for up to 32 actors, without gradients to the actor poses
+        (those take the torch bookkeeping below)."""
         if not self.has_actors or len(self.actor_grids) == 0 or len(self.actor_grids) > 32:
             return False
         a = self.config.actor
-        return a.num_levels == 4 and a.hashgrid_dim == 4 and not any(
-            p.requires_grad for p in getattr(self.actors, "parameters", lambda: [])()) 
+        dim = self.config.static.hashgrid_dim if proposal else 4
+        if proposal and self.config.static.num_levels < a.num_levels:
+            return False
+        return a.num_levels == 4 and a.hashgrid_dim == dim and not any(
+            p.requires_grad for p in getattr(self.actors, "parameters", lambda: [])())
 
     @torch.no_grad()
     def assign_actors(self, rays: F.RayData, iv: F.SampleIntervals, times: Tensor) -> "F.ActorBatch":

@@ -273,9 +273,16 @@ class NeuRADProposalField(nn.Module):
     def density_and_weights(self, ray_samples: RaySamples) -> Tuple[Tensor, Tensor]:
         """One kernel for get_density + RaySamples.get_weights: ([N,S,1], [N,S,1])."""
         rays, iv = per_ray_of(ray_samples)
-        if self.hashgrid.has_actors:  # unfused: the actor branch rewrites features between the grid and the decoder
+        if self.hashgrid.has_actors:
             if ray_samples.times is None:
                 raise ValueError("ray_samples.times is required in a scene with dynamic actors")
+            if self.hashgrid.can_assign_in_kernel(proposal=True):  # one assignment kernel + the fused round, no host sync
+                grid = self.hashgrid.static_grid
+                actors = self.hashgrid.assign_actors(rays, iv, ray_samples.times.reshape(rays.num_rays, -1)[:, 0])
+                dens, w = F.proposal_round(grid.hash_table, self.density_decoder.weight, rays, iv, grid.spec,
+                                           self.hashgrid.static_scale, actors=actors)
+                return dens.unsqueeze(-1), w.unsqueeze(-1)
+            # unfused: the torch bookkeeping rewrites features between the grid and the decoder
             feats, _ = self.hashgrid.encode_samples(rays, iv, ray_samples.times.reshape(rays.num_rays, -1)[:, 0])
             dens = trunc_exp(self.density_decoder(feats)).view(rays.num_rays, iv.num_samples)
             return dens.unsqueeze(-1), F.density_weights(dens, iv).unsqueeze(-1)

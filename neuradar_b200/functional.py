@@ -1016,7 +1016,7 @@ def carving_loss(weights: Tensor, iv: SampleIntervals, is_lidar: Tensor, directi
 class _ProposalRound(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, table, decoder_w, rays: RayData, iv: SampleIntervals, spec: GridSpec, scale: float):
+    def forward(ctx, table, decoder_w, rays: RayData, iv: SampleIntervals, spec: GridSpec, scale: float, actors, *actor_tables):
         ctx.sink = grad_sink_of(table)
         ctx.dec_sink = grad_sink_of(decoder_w)
         table = f32c(table)
@@ -1025,21 +1025,29 @@ class _ProposalRound(torch.autograd.Function):
         dev = table.device
         density = torch.empty((N, S), device=dev, dtype=torch.float32)
         weights = torch.empty_like(density)
-        train = any(ctx.needs_input_grad[:2])
+        train = any(ctx.needs_input_grad[:2]) or any(ctx.needs_input_grad[7:])
         feats = torch.empty((N, S, spec.out_dim), device=dev, dtype=torch.float32) if train else None
         pre = torch.empty((N, S), device=dev, dtype=torch.float32) if train else None
         g, r, i = spec.struct(table), rays.struct(), iv.struct()
+        ag = asmp = None
+        if actors is not None:
+            ctx.actor_sinks = [grad_sink_of(t) for t in actor_tables]
+            actors = ActorBatch(actors.grid_id, actors.pos, actors.std, actors.dirs, [f32c(t) for t in actor_tables], actors.spec)
+            ag, asmp = actors.grids_struct(), actors.samples_struct()
         _lib.call("nrb_proposal_fwd", C.byref(r), C.byref(g), ptr(dec), float(scale), C.byref(i), ptr(density),
-                                     ptr(weights), ptr(feats), ptr(pre), stream_ptr())
-        ctx.save_for_backward(table, dec, feats, pre)
+                  ptr(weights), ptr(feats), ptr(pre), None if ag is None else C.byref(ag),
+                  None if asmp is None else C.byref(asmp), stream_ptr())
+        extra = [] if actors is None else [actors.grid_id, actors.pos, actors.std, actors.dirs, *actors.tables]
+        ctx.save_for_backward(table, dec, feats, pre, *extra)
         ctx.rays, ctx.iv, ctx.spec, ctx.scale = rays, iv, spec, float(scale)
+        ctx.actor_spec = None if actors is None else actors.spec
         ctx.dec_shape = decoder_w.shape
         return density, weights
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, ddensity, dweights):
-        table, dec, feats, pre = ctx.saved_tensors
+        table, dec, feats, pre, *extra = ctx.saved_tensors
         dtable = ctx.sink if ctx.sink is not None else torch.zeros_like(table)
         ddec = ctx.dec_sink.reshape(-1) if ctx.dec_sink is not None else torch.zeros_like(dec)
         ddensity = None if ddensity is None else f32c(ddensity)
@@ -1047,16 +1055,32 @@ class _ProposalRound(torch.autograd.Function):
         g, r, i = ctx.spec.struct(table), ctx.rays.struct(), ctx.iv.struct()
         n_pts = ctx.rays.num_rays * ctx.iv.num_samples
         ws, ws_bytes = _workspace(int(_lib_().nrb_hash_bwd_workspace_bytes(C.byref(g), n_pts)), table.device)
+        ag = asmp = dptrs = None
+        dactor: List[Optional[Tensor]] = []
+        if ctx.actor_spec is not None:
+            actors = ActorBatch(extra[0], extra[1], extra[2], extra[3], list(extra[4:]), ctx.actor_spec)
+            ag, asmp = actors.grids_struct(), actors.samples_struct()
+            dactor = [sk if sk is not None else torch.zeros_like(t) for t, sk in zip(actors.tables, ctx.actor_sinks)]
+            dptrs = (C.c_void_p * len(dactor))(*[d.data_ptr() for d in dactor])
         _lib.call("nrb_proposal_bwd", C.byref(r), C.byref(g), ptr(dec), ctx.scale, C.byref(i), ptr(feats), ptr(pre),
-                  ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, stream_ptr())
+                  ptr(dweights), ptr(ddensity), ptr(dtable), ptr(ddec), ws, ws_bytes, None if ag is None else C.byref(ag),
+                  None if asmp is None else C.byref(asmp), dptrs, stream_ptr())
         if ctx.sink is not None:
             _sink_written(table)
+        if ctx.actor_spec is not None:
+            for t, sk in zip(actors.tables, ctx.actor_sinks):
+                if sk is not None:
+                    _sink_written(t)
+            dactor = [None if sk is not None else d for d, sk in zip(dactor, ctx.actor_sinks)]
         return ((None if ctx.sink is not None else dtable), (None if ctx.dec_sink is not None else ddec.reshape(ctx.dec_shape)),
-                None, None, None, None)
+                None, None, None, None, None, *dactor)
 
 
 def proposal_round(
-    table: Tensor, decoder_w: Tensor, rays: RayData, iv: SampleIntervals, spec: GridSpec, static_scale: float
+    table: Tensor, decoder_w: Tensor, rays: RayData, iv: SampleIntervals, spec: GridSpec, static_scale: float,
+    actors: Optional[ActorBatch] = None,
 ) -> Tuple[Tensor, Tensor]:
-    """One fused proposal round: (density [N,S], weights [N,S])."""
-    return _ProposalRound.apply(table, decoder_w, rays, iv, spec, static_scale)
+    """One fused proposal round: (density [N,S], weights [N,S]).  `actors` (from `actor_assign`): the samples inside actor
+    boxes read their actor's 4-level grid instead."""
+    extra = [] if actors is None else list(actors.tables)
+    return _ProposalRound.apply(table, decoder_w, rays, iv, spec, static_scale, actors, *extra)

@@ -687,3 +687,66 @@ def test_actor_path_has_no_host_sync(nb):
     fld.fused = False
     feats_torch = fld(rs)[nb.FieldHeadNames.FEATURE]
     assert rel_err(feats_kernel, feats_torch) <= 1e-5
+
+
+def test_proposal_round_with_actors_matches_torch_bookkeeping(nb):
+    """NeuRADProposalField in a scene with dynamic actors: the fused round with the in-kernel actor branch against the
+    torch bookkeeping of the same module (NeuRADHashEncoding._split_static_vs_actors + per-actor grids + zero padding,
+    neurad_encoding.py:160-187), forward and every gradient; and no host synchronisation on the kernel route."""
+    import neuradar_b200 as pkg
+    from neuradar_b200.synthetic import SyntheticActors, synthetic_rays
+
+    n, S = 384, 96
+    actors = SyntheticActors(16, device=DEV)
+    pcfg = pkg.NeuRADProposalFieldConfig()
+    pcfg.grid.static.log2_hashmap_size = 13
+    pcfg.grid.actor.log2_hashmap_size = 9
+    pcfg.grid.actor.flip_prob = 0.25
+    prop = pkg.NeuRADProposalField(pcfg, actors=actors, static_scale=100.0).to(DEV)
+    prop.train()
+    with torch.no_grad():
+        prop.hashgrid.static_grid.hash_table.mul_(2000.0)
+        for g in prop.hashgrid.actor_grids:
+            g.hash_table.mul_(2000.0)
+    r = synthetic_rays(n, seed=4)
+    centres = actors.centres[torch.arange(n // 2) % 16].cpu()
+    d = centres - r["origins"][: n // 2]
+    r["directions"][: n // 2] = d / d.norm(dim=-1, keepdim=True)
+    rb = nb.RayBundle(origins=r["origins"].to(DEV), directions=r["directions"].to(DEV), pixel_area=r["pixel_area"].to(DEV),
+                      times=r["times"].to(DEV), metadata={})
+    bins = (torch.linspace(0.5, 60.0, S + 1)[None, :].repeat(n, 1)).to(DEV)
+    rs = rb.get_ray_samples(bin_starts=bins[:, :-1, None], bin_ends=bins[:, 1:, None])
+    prop.hashgrid.ray_flip_override = (torch.rand(n, device=DEV) < 0.25).float() * -2 + 1
+    assert prop.hashgrid.can_assign_in_kernel(proposal=True)
+    gw = torch.randn((n, S, 1), device=DEV)
+    gd = torch.randn((n, S, 1), device=DEV) * 1e-3
+
+    def run():
+        for p in prop.parameters():
+            p.grad = None
+        dens, w = prop.density_and_weights(rs)
+        ((w * gw).sum() + (dens * gd).sum()).backward()
+        return dens.detach(), w.detach(), {k: p.grad.clone() for k, p in prop.named_parameters() if p.grad is not None}
+
+    run()
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        dens_k, w_k, grads_k = run()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    rays, iv = rs.per_ray()
+    inside = int((prop.hashgrid.assign_actors(rays, iv, rs.times.reshape(n, -1)[:, 0]).grid_id >= 0).sum())
+    assert inside > 100, inside
+    prop.hashgrid.can_assign_in_kernel = lambda proposal=False: False
+    dens_t, w_t, grads_t = run()
+    assert rel_err(dens_k, dens_t) <= 1e-5 and rel_err(w_k, w_t) <= 1e-5
+    assert set(grads_k) == set(grads_t)
+    nonzero_actor_tables = 0
+    for k in grads_t:
+        if float(grads_t[k].abs().max()) == 0.0:
+            assert float(grads_k[k].abs().max()) == 0.0, k
+            continue
+        assert rel_err(grads_k[k], grads_t[k]) <= 1e-4, (k, rel_err(grads_k[k], grads_t[k]))
+        nonzero_actor_tables += "actor_grids" in k
+    assert nonzero_actor_tables >= 4
