@@ -348,6 +348,10 @@ class NeuRADHashEncoding(nn.Module):
         dirs = rays.directions[:, None, :].expand(-1, iv.num_samples, -1)
         return self._apply_actors(feats, mean, wstd, dirs, times.reshape(-1))
 
+    pose_cache: Optional[dict] = None
+    """Set by the owner of several encodings that see the same rays within one step (NeuRadarHotPath: the field and the
+    proposal networks): the actor poses at the rays' times are then computed once per step instead of once per encoding."""
+
     ray_flip_override: Optional[Tensor] = None
     """Tests: replay a recorded per-ray mirror draw ([N] of +1 / -1) instead of drawing one."""
 
@@ -375,8 +379,17 @@ class NeuRADHashEncoding(nn.Module):
     @torch.no_grad()
     def assign_actors(self, rays: F.RayData, iv: F.SampleIntervals, times: Tensor) -> "F.ActorBatch":
         """Which samples fall into which actor box, in one kernel (csrc/actors.cu): no nonzero(), no host synchronisation."""
-        boxes2world, valid = self.actors.get_boxes2world(times.reshape(-1), flatten=False)
-        world2boxes = _pose_inverse(boxes2world)
+        key = (times.data_ptr(), times._version, tuple(times.shape))
+        cached = None if self.pose_cache is None else self.pose_cache.get(key)
+        if cached is None:
+            boxes2world, valid = self.actors.get_boxes2world(times.reshape(-1), flatten=False)
+            # (R^T | -R^T t) element-wise: a matmul over [N, A] 3x3 blocks becomes A batched cuBLAS gemv launches
+            Ri = boxes2world[..., :3, :3].transpose(-2, -1)
+            world2boxes = torch.cat([Ri, -(Ri * boxes2world[..., None, :3, 3]).sum(-1, keepdim=True)], dim=-1).contiguous()
+            cached = (world2boxes, valid, times)  # (times is held so that its address cannot be recycled under the key)
+            if self.pose_cache is not None:
+                self.pose_cache[key] = cached
+        world2boxes, valid = cached[0], cached[1]
         flip = self._draw_flip(rays.num_rays, rays.origins.device)
         grid_id, pos, std, dirs = F.actor_assign(rays, iv, world2boxes, valid, self.actors.actor_bounds(), self.actors.actor_to_id,
                                                  flip, self.actor_scale)

@@ -150,6 +150,17 @@ class NeuRadarHotPath(nn.Module):
 
     def get_nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool = False) -> Dict[str, Tensor]:
         self._scale_pixel_area(ray_bundle)
+        grids = [self.field.hashgrid] + [p.hashgrid for p in self.proposal_fields]
+        poses: dict = {}
+        for h in grids:  # the actor poses at the rays' times are shared by the three encodings of this step
+            h.pose_cache = poses
+        try:
+            return self._nff_outputs(ray_bundle, calc_lidar_losses)
+        finally:
+            for h in grids:
+                h.pose_cache = None
+
+    def _nff_outputs(self, ray_bundle: RayBundle, calc_lidar_losses: bool) -> Dict[str, Tensor]:
         ray_samples, proposal_ray_samples, proposal_weights = self._get_ray_samples(ray_bundle)
         if self.field.can_render(ray_samples):
             # field + _render_weights + AccumulationRenderer + sky fix-up + FeatureRenderer + render_depth_simple as ONE

@@ -30,12 +30,14 @@ class ReferencePath:
 
     def __init__(self, main: Tuple[int, int, int, int, int] = (16, 2, 19, 16, 1024), prop_log2: int = 20,
                  proposal_samples: Tuple[int, ...] = (64, 48), nerf_samples: int = 48, static_scale: float = 100.0,
-                 seed: int = 42, late_binding: bool = True):
+                 seed: int = 42, late_binding: bool = True, actors=None):
+        """`actors`: None (the reference's own DynamicActors with no trajectories) or an object with the interface
+        NeuRADHashEncoding uses (n_actors, get_boxes2world, actor_bounds, actor_to_id), e.g. synthetic.SyntheticActors."""
         self.root = ref_shim.install()
         with contextlib.redirect_stdout(sys.stderr):  # the reference print()s notices; stdout belongs to the caller
-            self._build(main, prop_log2, proposal_samples, nerf_samples, static_scale, seed, late_binding)
+            self._build(main, prop_log2, proposal_samples, nerf_samples, static_scale, seed, late_binding, actors)
 
-    def _build(self, main, prop_log2, proposal_samples, nerf_samples, static_scale, seed, late_binding):
+    def _build(self, main, prop_log2, proposal_samples, nerf_samples, static_scale, seed, late_binding, actors=None):
         from nerfstudio.field_components.neurad_encoding import NeuRADHashEncodingConfig, StaticSettings
         from nerfstudio.fields.neurad_field import (NeuRADField, NeuRADFieldConfig, NeuRADProposalField,
                                                      NeuRADProposalFieldConfig)
@@ -44,7 +46,8 @@ class ReferencePath:
 
         torch.manual_seed(seed)
         L, F, T, r0, r1 = main
-        actors = DynamicActors(DynamicActorsConfig(), trajectories=[])
+        if actors is None:
+            actors = DynamicActors(DynamicActorsConfig(), trajectories=[])
         fcfg = NeuRADFieldConfig()
         fcfg.grid = NeuRADHashEncodingConfig(
             static=StaticSettings(hashgrid_dim=F, num_levels=L, base_res=r0, max_res=r1, log2_hashmap_size=T),
