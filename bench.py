@@ -489,8 +489,6 @@ def run_b200(args, rank, world, local_rank):
         "nrb_proposal_bwd": ("hbm", n / passes * prop_mean * 192.0, 0.0),
         "nrb_alpha_composite_fwd": ("hbm", n_main * 32 * 4.0, 0.0),
         "nrb_alpha_composite_bwd": ("hbm", n_main * 32 * 4.0, 0.0),
-        "nrb_field_mlp_fwd": ("tensor", n_main * float(mlp_flop), 0.0),
-        "nrb_field_mlp_bwd": ("tensor", n_main * float(mlp_flop) * 2, 0.0),
     }
     if args.optimizer:  # read p, g, m, v + write p, m, v, g = 32 B per parameter, averaged over the two groups' launches
         work["nrb_adam_step"] = ("hbm", arena_bytes / 4 * 32.0 / 2, 0.0)

@@ -124,62 +124,27 @@ int nrb_mlp_fwd(const nrb_mlp_t* mlp, const float* x, float* y, float* hidden, i
 int nrb_mlp_bwd(const nrb_mlp_t* mlp, const float* x, const float* hidden, const float* dy, float* dx,
                 const nrb_mlp_grad_t* grads, int64_t M, nrb_stream_t stream);
 
-/* ---- fused NeuRAD field MLP on tcgen05 tensor cores: everything NeuRADField.forward does after the hash grid
- * (fields/neurad_field.py:132-152; replaces the two tcnn FullyFusedMLP networks, mlp.py:109-127):
+/* ---- the NeuRAD field's two MLPs (fields/neurad_field.py:132-152; they replace the two tcnn FullyFusedMLP networks,
+ * mlp.py:109-127), as the fused field kernels below evaluate them:
  *   geo = mlp_geo(x) [32 -> 32 ReLU -> 33]; sdf, emb = split(geo, [1, 32]);
  *   feature = emb + mlp_feature([emb, sh]) [48 -> 32 ReLU -> 32 ReLU -> 32]; alpha = sigmoid(-sdf (|beta| + beta_min)).
  * weights[0..1] = mlp_geo.layers.{0,1}.weight, weights[2..4] = mlp_feature.layers.{0,1,2}.weight ([out,in] row-major),
- * biases likewise (may be NULL); x [M,32] hash features; sh [N_rays,16] SH basis of each ray's direction, row m of x
- * belongs to ray m / samples_per_ray.  fp32 in and out; products are evaluated as 3xTF32 with fp32 accumulation. */
+ * biases likewise (may be NULL). */
 typedef struct {
   const float* weights[5];
   const float* biases[5];
   const float* beta;
   float beta_min;
 } nrb_field_mlp_t;
-/* Activations the backward pass needs.  Feature-major: element (feature j, sample m) at [j * ld + m], with
- * ld = nrb_field_saved_ld(M) (M rounded up to the 128-sample tile); masks [3][ld] hold one bit per ReLU unit of
- * h1 / g1 / g2.  Pass NULL (or h1 == NULL) for inference. */
-typedef struct {
-  float* h1;
-  float* emb;
-  float* g1;
-  float* g2;
-  uint32_t* masks;
-  int64_t ld;
-} nrb_field_saved_t;
+/* Leading dimension of the per-sample buffers the fused kernels keep: M rounded up to the 128-sample tile. */
 int64_t nrb_field_saved_ld(int64_t M);
-int nrb_field_mlp_fwd(const nrb_field_mlp_t* mlp, const float* x, const float* sh, int32_t samples_per_ray, int64_t M,
-                      float* feature, float* sdf, float* alpha, const nrb_field_saved_t* saved, nrb_stream_t stream);
-/* Backward of nrb_field_mlp_fwd.  Inputs: the forward input x, the saved activations, sh, the forward outputs sdf and
- * alpha, and the upstream gradients dfeature [M,32], dsdf [M] (optional) and dalpha [M] (optional).
- * Outputs: dx [M,32] (optional, gradient w.r.t. the hash features), and ACCUMULATED parameter gradients: dweights[i]
- * / dbiases[i] shaped like the parameters (each optional) and dbeta [1] = d loss / d(|beta| + beta_min). */
-typedef struct {
-  const float* x;
-  nrb_field_saved_t saved;
-  const float* sh;
-  const float* sdf;
-  const float* alpha;
-  const float* dfeature;
-  const float* dsdf;
-  const float* dalpha;
-} nrb_field_bwd_in_t;
-typedef struct {
-  float* dx;
-  float* dweights[5];
-  float* dbiases[5];
-  float* dbeta;
-} nrb_field_bwd_out_t;
-int nrb_field_mlp_bwd(const nrb_field_mlp_t* mlp, const nrb_field_bwd_in_t* in, const nrb_field_bwd_out_t* out,
-                      int32_t samples_per_ray, int64_t M, nrb_stream_t stream);
 /* ---- fused field: hash-grid gather + geometry MLP + feature MLP in one kernel, backward with recomputed activations
- * (round 2; replaces the nrb_hash_fwd -> nrb_field_mlp_fwd pair and nrb_field_mlp_bwd -> nrb_hash_bwd on the training
- * path: NeuRADHashEncoding.forward + NeuRADField.forward, neurad_encoding.py:152-189, neurad_field.py:128-152).
+ * (NeuRADHashEncoding.forward + NeuRADField.forward in one launch, neurad_encoding.py:152-189, neurad_field.py:128-152).
  * Forward: pass EITHER `grid` with the contracted sample means xyz [M,3] and stds std [M] (or NULL) from
  * nrb_frustum_gaussians - the 32 hash features (num_levels * features_per_level == 32, 2 or 4 features per level) are
  * gathered inside the kernel and never written - OR the hash features x [M,32] (grid == NULL; scenes with actors).
- * Outputs as nrb_field_mlp_fwd.  For training pass `saved`: ximg receives the bf16 hi / mid operand image of the hash
+ * x and sh [N_rays,16] (the SH basis of each ray's direction; row m belongs to ray m / samples_per_ray) are fp32, as are
+ * the outputs feature [M,32], sdf [M], alpha [M]; products are evaluated as 3xTF32 with fp32 accumulation.  For training pass `saved`: ximg receives the bf16 hi / mid operand image of the hash
  * features (nrb_field_fused_image_bytes(M) bytes: 16 KB per 128-sample tile) and masks [3][ld] one bit per ReLU unit of
  * the three hidden layers, ld = nrb_field_saved_ld(M).  Nothing else is kept: the backward recomputes the activations. */
 typedef struct {
@@ -216,7 +181,7 @@ int nrb_field_fused_fwd(const nrb_field_mlp_t* mlp, const nrb_grid_t* grid, cons
  * dfeat_ray[m / samples_per_ray].  dsdf / dalpha [M] are optional.  dximg (optional) receives the gradient with
  * respect to the hash features as a tile image: float4 element (tile, chunk c of 4 features, sample r of the tile) at
  * [(tile * 8 + c) * 128 + r] (nrb_field_fused_image_bytes(M) * 1 bytes); nrb_hash_bwd_image scatters it into the table.
- * Parameter gradients are ACCUMULATED as in nrb_field_mlp_bwd, except that dbeta [1] is the gradient with respect to
+ * Parameter gradients (dweights[i] / dbiases[i] shaped like the parameters, each optional) are ACCUMULATED; dbeta [1] is the gradient with respect to
  * beta itself (the sign of beta is applied inside). */
 typedef struct {
   nrb_field_fused_saved_t saved;
@@ -259,10 +224,6 @@ int nrb_actor_assign(const nrb_rays_t* rays, const nrb_intervals_t* iv, const fl
 int nrb_actor_scatter(const nrb_actor_grids_t* grids, float* const* dtables, const nrb_actor_samples_t* samples,
                       const float* dyimg, float* dpos, int64_t M, nrb_stream_t stream);
 
-/* Debug probe of the UMMA descriptor conventions: P, Q [128,32] are staged as canonical tiles, a chain of tf32 MMAs
- * is issued with cfg = {a_major, b_major, M, N, a_lbo, a_sbo, a_step, b_lbo, b_sbo, b_step, ksteps} (host ints) and the
- * [128 lanes][32 columns] accumulator block is written to dump. */
-int nrb_tc_probe(const float* P, const float* Q, const int32_t* cfg11, float* dump, nrb_stream_t stream);
 /* One linear layer y = x W^T + b (optional ReLU) through the same tcgen05 building blocks (K = 32 or 48,
  * n_out <= 48): the unit test of the descriptor / layout conventions. */
 int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,

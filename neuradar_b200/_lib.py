@@ -77,21 +77,6 @@ class FieldMlp(C.Structure):
     ]
 
 
-class FieldSaved(C.Structure):
-    _fields_ = [("h1", C.c_void_p), ("emb", C.c_void_p), ("g1", C.c_void_p), ("g2", C.c_void_p), ("masks", C.c_void_p),
-                ("ld", C.c_int64)]
-
-
-class FieldBwdIn(C.Structure):
-    _fields_ = [("x", C.c_void_p), ("saved", FieldSaved)] + [
-        (n, C.c_void_p) for n in ("sh", "sdf", "alpha", "dfeature", "dsdf", "dalpha")
-    ]
-
-
-class FieldBwdOut(C.Structure):
-    _fields_ = [("dx", C.c_void_p), ("dweights", C.c_void_p * 5), ("dbiases", C.c_void_p * 5), ("dbeta", C.c_void_p)]
-
-
 class FieldFusedSaved(C.Structure):  # nrb_field_fused_saved_t
     _fields_ = [("ximg", C.c_void_p), ("masks", C.c_void_p), ("ld", C.c_int64)]
 
@@ -147,11 +132,8 @@ SIGNATURES = {
     "nrb_mlp_fwd": [C.POINTER(Mlp), _P, _P, _P, _I64, _P],
     "nrb_mlp_bwd": [C.POINTER(Mlp), _P, _P, _P, _P, C.POINTER(MlpGrad), _I64, _P],
     "nrb_sh16": [_P, _P, _I64, _I32, _P],
-    "nrb_field_mlp_fwd": [C.POINTER(FieldMlp), _P, _P, _I32, _I64, _P, _P, _P, C.POINTER(FieldSaved), _P],
     "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],
     "nrb_field_saved_ld": [_I64],
-    "nrb_field_mlp_bwd": [C.POINTER(FieldMlp), C.POINTER(FieldBwdIn), C.POINTER(FieldBwdOut), _I32, _I64, _P],
-    "nrb_tc_probe": [_P, _P, C.POINTER(C.c_int32), _P, _P],
     "nrb_field_fused_image_bytes": [_I64],
     "nrb_field_fused_fwd": [C.POINTER(FieldMlp), C.POINTER(Grid), _P, _P, _P, _P, _I32, _I64, _P, _P, _P,
                             C.POINTER(FieldFusedSaved), C.POINTER(ActorGrids), C.POINTER(ActorSamples), _P],

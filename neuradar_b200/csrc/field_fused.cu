@@ -1024,6 +1024,8 @@ static int make_rows_tensor_map(CUtensorMap* map, const float* base, int64_t M) 
   return NRB_OK;
 }
 
+extern "C" int64_t nrb_field_saved_ld(int64_t M) { return (M + tc::kRows - 1) / tc::kRows * tc::kRows; }
+
 extern "C" int64_t nrb_field_fused_image_bytes(int64_t M) { return (M + tc::kRows - 1) / tc::kRows * 16384; }
 
 extern "C" int nrb_field_fused_fwd(const nrb_field_mlp_t* p, const nrb_grid_t* grid, const float* xyz, const float* std,

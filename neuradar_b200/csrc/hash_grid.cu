@@ -270,9 +270,9 @@ extern "C" int nrb_hash_fwd(const nrb_grid_t* grid, const float* x, const float*
   const GridDev g = to_dev(grid);
   auto s = static_cast<cudaStream_t>(stream);
   const unsigned blocks = blocks_for(total, 256);
-  static const bool rows = env_or("NRB_HASH_FWD_ROWS", 1.0) != 0.0;
   const int row_floats = grid->num_levels * grid->features_per_level;
-  if (rows && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
+  // power-of-two row widths (the field grids): warp-transposed rows kernel; other shapes (L6/F1 proposals, tiny M): generic
+  if (row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
     const size_t smem = static_cast<size_t>(kFwdWarps) * 32 * row_floats * 4;
     const unsigned nb = blocks_for(M, kFwdWarps * 32);
 #define NRB_ROWS(F)                                                                                                    \
@@ -325,9 +325,8 @@ static int launch_hash_bwd(const nrb_grid_t* grid, const GridDev& g, const float
   if (int rc = prepare_bwd_plan(grid, M, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
   const int64_t total = M * grid->num_levels;
   const unsigned blocks = blocks_for(total, 256);
-  static const bool dedup = env_or("NRB_HASH_BWD_DEDUP", 1.0) != 0.0;
   const int row_floats = grid->num_levels * F;
-  if (dedup && dx == nullptr && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
+  if (dx == nullptr && row_floats >= 4 && row_floats <= 64 && (row_floats & (row_floats - 1)) == 0 && M >= 32) {
     const size_t smem = static_cast<size_t>(kDedupWarps) * 32 * row_floats * 4;
     cudaError_t e = ensure_dynamic_smem(reinterpret_cast<const void*>(hash_bwd_dedup_kernel<F>), 64 * 1024);
     NRB_REQUIRE(e == cudaSuccess, static_cast<int>(e), "nrb_hash_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));

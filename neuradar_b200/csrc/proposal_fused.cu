@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     const __grid_constant__ PropGrid g, const __grid_constant__ BwdPlan plan, const float* __restrict__ origins, const float* __restrict__ directions,
     const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
     const float* __restrict__ saved_feats, const float* __restrict__ saved_pre, const float* __restrict__ dweights,
-    const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder, int merge) {
+    const float* __restrict__ ddensity, float* __restrict__ dtable, float* __restrict__ ddecoder) {
   __shared__ float s_ddec[NRB_MAX_LEVELS * 4];
   __shared__ float s_dec[NRB_MAX_LEVELS * 4];
   const int lane = threadIdx.x & 31;
@@ -226,16 +226,13 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
             }
             float w8[8];
             corner_weights(cell, w8);
-            if (merge) {
-              float v[8][F];
+            // runs of adjacent samples of the ray that share a cell are summed before scattering (hash_bwd_plan.cuh)
+            float v[8][F];
 #pragma unroll
-              for (int k = 0; k < 8; ++k)
+            for (int k = 0; k < 8; ++k)
 #pragma unroll
-                for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
-              merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act_static, lane, dtable, spread);
-            } else if (act_static) {
-              scatter_corners<F>(plan, l, g.log2_size, scal, q.x, q.y, q.z, cell, gr, w8, dtable, spread);
-            }
+              for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
+            merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act_static, lane, dtable, spread);
           }
         }
       }
@@ -341,12 +338,10 @@ extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
   BwdPlan plan;
   int64_t vertices = 0;
   if (int rc = prepare_bwd_plan(grid, N * iv->num_samples, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
-  // merge runs of adjacent samples of a ray that share a cell before scattering (hash_bwd_plan.cuh)
-  static const int merge = env_or("NRB_PROP_BWD_MERGE", 1.0) != 0.0 ? 1 : 0;
 #define NRB_LAUNCH(F)                                                                                              \
   proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, plan, rays->origins, rays->directions, rays->pixel_area,  \
                                                             static_scale, *iv, N, saved_feats, saved_pre,          \
-                                                            dweights, ddensity, dtable, ddecoder_w, merge)
+                                                            dweights, ddensity, dtable, ddecoder_w)
   switch (grid->features_per_level) {
     case 1: NRB_LAUNCH(1); break;
     case 2: NRB_LAUNCH(2); break;

@@ -6,7 +6,6 @@ Field base API (`get_density`, `get_outputs`, `forward`) <- nerfstudio/fields/ba
 """
 from __future__ import annotations
 
-import os
 from dataclasses import dataclass, field
 from enum import Enum
 from typing import Dict, Optional, Tuple, Type
@@ -117,16 +116,6 @@ class NeuRADField(nn.Module):
             and (c.geo_hidden_dim, c.geo_num_layers, c.nff_hidden_dim, c.nff_num_layers, c.nff_out_dim) == (32, 2, 32, 3, 32)
         )
 
-    ray_chunks = int(os.environ.get("NRB_RAY_CHUNKS", "1"))
-    """Training only, optional (default 1 = off): process the rays in this many chunks on two alternating side
-    streams.  Autograd replays each chunk's backward on its forward stream, so one chunk's table scatter could overlap
-    with the next chunk's tensor-core MLP backward.  Measured on B200 (config 2): 11.97 ms/step unchunked, 11.71 ms
-    with 2 chunks, 12.9 ms with 4 (per-chunk workspace clears and folds eat the overlap) - left off."""
-
-    fused = os.environ.get("NRB_FIELD_FUSED", "1") != "0"
-    """One kernel for hash gather + both MLPs, backward with recomputed activations (csrc/field_fused.cu).  0 selects
-    the round-1 kernel chain (nrb_hash_fwd -> nrb_field_mlp_fwd, saved activations) for A/B measurements."""
-
     def _field_chunk(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
         """hash encode + everything after it (ONE tcgen05 kernel forward, one backward) for a set of rays."""
         geo_l, feat_l = self.mlp_geo.layers, self.mlp_feature.layers
@@ -135,7 +124,7 @@ class NeuRADField(nn.Module):
         beta, beta_min = self.sdf_to_density.beta, self.sdf_to_density.beta_min_value
         grid = self.hashgrid.static_grid
         with_actors = self.hashgrid.has_actors and times is not None
-        if self.fused and grid.features_per_level in (2, 4) and (not with_actors or self.hashgrid.can_assign_in_kernel()):
+        if grid.features_per_level in (2, 4) and (not with_actors or self.hashgrid.can_assign_in_kernel()):
             # the 32 hash features are gathered inside the MLP kernel and never reach HBM; samples inside an actor box
             # (assigned by one kernel) read their actor's grid there
             x3, std = F.frustum_gaussians(rays, iv, self.hashgrid.static_scale)
@@ -150,14 +139,12 @@ class NeuRADField(nn.Module):
         else:  # some samples were rotated into an actor frame: one SH row per sample
             sh = self.direction_encoding(get_normalized_directions(sample_dirs.reshape(-1, 3)))
             sh_group = 1
-        if self.fused:
-            return F.field_fused(None, features, None, None, sh, sh_group, None, weights, biases, beta, beta_min)
-        return F.field_mlp(features, sh, sh_group, weights, biases, beta, beta_min)
+        return F.field_fused(None, features, None, None, sh, sh_group, None, weights, biases, beta, beta_min)
 
     def can_render(self, ray_samples: RaySamples) -> bool:
         """True when `render` applies: default field shape, a 32-feature static grid and no dynamic actors."""
         grid = self.hashgrid.static_grid
-        return (self.fused and self._tensor_core_path() and grid.features_per_level in (2, 4) and len(ray_samples.shape) == 2
+        return (self._tensor_core_path() and grid.features_per_level in (2, 4) and len(ray_samples.shape) == 2
                 and (not self.hashgrid.has_actors or (self.hashgrid.can_assign_in_kernel() and ray_samples.times is not None)))
 
     def render(self, ray_samples: RaySamples, trans_eps: float = 0.0):
@@ -176,32 +163,6 @@ class NeuRADField(nn.Module):
         return F.field_render(grid.hash_table, x3, std, sh, iv, grid.spec, weights, biases, self.sdf_to_density.beta,
                               self.sdf_to_density.beta_min_value, trans_eps, actors)
 
-    def _forward_tensor_core(self, rays: F.RayData, iv: F.SampleIntervals, times: Optional[Tensor] = None):
-        N = rays.num_rays
-        k = self.ray_chunks if (torch.is_grad_enabled() and self.training and N >= 8192 * self.ray_chunks) else 1
-        if k <= 1 or self.hashgrid.has_actors:
-            return self._field_chunk(rays, iv, times)
-        dev = rays.origins.device
-        main = torch.cuda.current_stream(dev)
-        bounds = [(N * i) // k for i in range(k + 1)]
-        parts = []
-        for i in range(k):
-            lo, hi = bounds[i], bounds[i + 1]
-            sub = F.RayData(rays.origins[lo:hi], rays.directions[lo:hi], rays.pixel_area[lo:hi])
-            sub_iv = F.SampleIntervals(iv.starts[lo:hi], iv.ends[lo:hi])
-            side = F.side_stream(dev, i % 2)
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                parts.append(self._field_chunk(sub, sub_iv))
-        outs = []
-        for s in (F.side_stream(dev, 0), F.side_stream(dev, 1)):
-            main.wait_stream(s)
-        for j in range(3):
-            for p in parts:
-                p[j].record_stream(main)
-            outs.append(torch.cat([p[j] for p in parts], dim=0))
-        return tuple(outs)
-
     def forward(self, ray_samples: RaySamples, compute_normals: bool = False) -> Dict[FieldHeadNames, Tensor]:
         if compute_normals:
             raise NotImplementedError("normals are not rendered on the NeuRadar path")
@@ -214,7 +175,7 @@ class NeuRADField(nn.Module):
                 raise ValueError("ray_samples.times is required in a scene with dynamic actors")
             times = ray_samples.times.reshape(N, -1)[:, 0]
         if self._tensor_core_path():
-            feature, sdf, alpha = self._forward_tensor_core(rays, iv, times)
+            feature, sdf, alpha = self._field_chunk(rays, iv, times)
             return {
                 FieldHeadNames.FEATURE: feature.view(*shape, 32),
                 FieldHeadNames.SDF: sdf.view(*shape, 1),

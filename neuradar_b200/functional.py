@@ -345,119 +345,6 @@ def _field_struct(weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]],
     return m
 
 
-def _alloc_field_saved(M: int, dev):
-    """Feature-major activation buffers [32, ld] x 4 and the ReLU bit masks [3, ld] (see nrb_field_saved_t)."""
-    ld = int(_lib_().nrb_field_saved_ld(M))
-    acts = [torch.empty((32, ld), device=dev, dtype=torch.float32) for _ in range(4)]
-    masks = torch.empty((3, ld), device=dev, dtype=torch.int32)
-    return acts + [masks]
-
-
-def _fill_saved(sv, saved) -> None:
-    sv.h1, sv.emb, sv.g1, sv.g2, sv.masks = (ptr(t) for t in saved)
-    sv.ld = saved[0].shape[1]
-
-
-def field_mlp_forward(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Tensor],
-                      biases: Sequence[Optional[Tensor]], beta: Tensor, beta_min: float, save: bool = False):
-    """Inference-only entry of the fused tensor-core field MLP: (feature [M,32], sdf [M], alpha [M], saved)."""
-    x, sh = f32c(x), f32c(sh)
-    weights = [f32c(w) for w in weights]
-    biases = [None if b is None else f32c(b) for b in biases]
-    beta = f32c(beta)
-    M = x.shape[0]
-    dev = x.device
-    feature = torch.empty((M, 32), device=dev, dtype=torch.float32)
-    sdf = torch.empty((M,), device=dev, dtype=torch.float32)
-    alpha = torch.empty((M,), device=dev, dtype=torch.float32)
-    saved = None
-    sv = _lib.FieldSaved()
-    if save:
-        saved = _alloc_field_saved(M, dev)
-        _fill_saved(sv, saved)
-    m = _field_struct(weights, biases, beta, beta_min)
-    _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
-              ptr(alpha), C.byref(sv), stream_ptr())
-    return feature, sdf, alpha, saved
-
-
-def tc_probe(P: Tensor, Q: Tensor, cfg: Sequence[int]) -> Tensor:
-    """Descriptor-convention probe (see nrb_tc_probe): returns the [128, 32] accumulator dump."""
-    P, Q = f32c(P), f32c(Q)
-    dump = torch.full((128, 32), -1.0, device=P.device, dtype=torch.float32)
-    arr = (C.c_int32 * 11)(*[int(v) for v in cfg])
-    _lib.call("nrb_tc_probe", ptr(P), ptr(Q), arr, ptr(dump), stream_ptr())
-    return dump
-
-
-class _FieldMlp(torch.autograd.Function):
-    """Fused tensor-core field MLP with its hand-written backward.  Inputs: x [M,32], sh [N,16], beta [1], then the
-    five weights and five biases; outputs feature [M,32], sdf [M], alpha [M]."""
-
-    @staticmethod
-    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, sh, samples_per_ray: int, beta_min: float, beta, *params):
-        x, sh, beta = f32c(x), f32c(sh.detach()), f32c(beta)
-        weights = [f32c(w) for w in params[:5]]
-        biases = [None if b is None else f32c(b) for b in params[5:]]
-        M, dev = x.shape[0], x.device
-        feature = torch.empty((M, 32), device=dev, dtype=torch.float32)
-        sdf = torch.empty((M,), device=dev, dtype=torch.float32)
-        alpha = torch.empty((M,), device=dev, dtype=torch.float32)
-        train = any(ctx.needs_input_grad)
-        sv = _lib.FieldSaved()
-        saved = []
-        if train:
-            saved = _alloc_field_saved(M, dev)
-            _fill_saved(sv, saved)
-        m = _field_struct(weights, biases, beta, beta_min)
-        _lib.call("nrb_field_mlp_fwd", C.byref(m), ptr(x), ptr(sh), int(samples_per_ray), M, ptr(feature), ptr(sdf),
-                  ptr(alpha), C.byref(sv), stream_ptr())
-        if train:
-            ctx.save_for_backward(x, sh, beta, sdf, alpha, *saved, *weights, *[b for b in biases if b is not None])
-            ctx.has_bias = [b is not None for b in biases]
-            ctx.samples_per_ray, ctx.beta_min = int(samples_per_ray), float(beta_min)
-        return feature, sdf, alpha
-
-    @staticmethod
-    @custom_bwd(device_type="cuda")
-    def backward(ctx, dfeature, dsdf, dalpha):
-        t = ctx.saved_tensors
-        x, sh, beta, sdf, alpha = t[:5]
-        saved = list(t[5:10])
-        weights = list(t[10:15])
-        rest = list(t[15:])
-        biases = [rest.pop(0) if hb else None for hb in ctx.has_bias]
-        M = x.shape[0]
-        dfeature = torch.zeros_like(x) if dfeature is None else f32c(dfeature)
-        dsdf = None if dsdf is None else f32c(dsdf)
-        dalpha = None if dalpha is None else f32c(dalpha)
-        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dws = [torch.zeros_like(w) for w in weights]
-        dbs = [None if b is None else torch.zeros_like(b) for b in biases]
-        dbeta_eff = torch.zeros((1,), device=x.device, dtype=torch.float32)
-        m = _field_struct(weights, biases, beta, ctx.beta_min)
-        bi = _lib.FieldBwdIn()
-        bi.x, bi.sh = ptr(x), ptr(sh)
-        _fill_saved(bi.saved, saved)
-        bi.sdf, bi.alpha, bi.dfeature, bi.dsdf, bi.dalpha = ptr(sdf), ptr(alpha), ptr(dfeature), ptr(dsdf), ptr(dalpha)
-        bo = _lib.FieldBwdOut()
-        bo.dx = ptr(dx)
-        for i in range(5):
-            bo.dweights[i] = ptr(dws[i])
-            bo.dbiases[i] = ptr(dbs[i])
-        bo.dbeta = ptr(dbeta_eff)
-        _lib.call("nrb_field_mlp_bwd", C.byref(m), C.byref(bi), C.byref(bo), ctx.samples_per_ray, M, stream_ptr())
-        dbeta = dbeta_eff * torch.sign(beta)  # d(|beta| + beta_min) / d beta
-        return (dx, None, None, None, dbeta.view_as(beta), *dws, *dbs)
-
-
-def field_mlp(x: Tensor, sh: Tensor, samples_per_ray: int, weights: Sequence[Tensor], biases: Sequence[Optional[Tensor]],
-              beta: Tensor, beta_min: float) -> Tuple[Tensor, Tensor, Tensor]:
-    """NeuRADField after the hash grid, fused on the tensor cores: (feature [M,32], sdf [M], alpha [M])."""
-    return _FieldMlp.apply(x, sh, samples_per_ray, beta_min, beta, *weights, *biases)
-
-
 # ------------------------------------------------------------------------------------------------
 # dynamic actors: per-sample assignment (no compaction, no host synchronisation)
 # ------------------------------------------------------------------------------------------------

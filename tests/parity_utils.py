@@ -101,6 +101,13 @@ def rel_err(a: Tensor, b: Tensor) -> float:
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
+def outside_bar(a: Tensor, b: Tensor, rel: float = 1e-3) -> int:
+    """Number of elements that break the element-wise parity bar of north_star: |a - b| <= rel * |b| + rel * rms(b)."""
+    a, b = a.detach().double().cpu().reshape(-1), b.detach().double().cpu().reshape(-1)
+    rms = float(b.pow(2).mean().sqrt())
+    return int(((a - b).abs() > rel * b.abs() + rel * rms).sum())
+
+
 def run_path_parity(num_rays: int = 256, device: str = "cuda:0", seed: int = 3, train: bool = True,
                     log2_main: int = 14, log2_prop: int = 14, tol: float = 1e-3, with_losses: bool = False) -> Dict[str, object]:
     """Run the CUDA hot path and the CPU oracle on the same rays, parameters and jitter; compare everything.
