@@ -54,10 +54,13 @@ __global__ void __launch_bounds__(kRows) tc_linear_kernel(const float* __restric
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
-    if (t == 0) {
-      fence_after_sync();
-      issue_gemm(tmem_base, 128, N, smem_u32(a_hi), smem_u32(a_lo), K, smem_u32(w_hi), smem_u32(w_lo), K, K, false);
-      mma_commit(mbar);
+    if (warp == 0) {  // one elected lane of a converged warp issues (straight-line UTCHMMA sequence, see elect_one)
+      if (elect_one()) {
+        fence_after_sync();
+        issue_gemm(tmem_base, 128, N, smem_u32(a_hi), smem_u32(a_lo), K, smem_u32(w_hi), smem_u32(w_lo), K, K, false);
+        mma_commit(mbar);
+      }
+      __syncwarp();
     }
     mbar_wait(mbar, phase);
     phase ^= 1;

@@ -151,3 +151,34 @@ def test_direct_scatter_into_arena_matches_autograd_accumulation():
     scale = float(grads[0].abs().max())
     assert scale > 0
     assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * scale  # atomics: last-bit differences only
+
+
+def test_direct_scatter_from_a_side_stream_is_ordered_before_the_default_stream():
+    """A backward that ran on a side stream (autograd replays a node on its forward's stream) and added straight into a
+    gradient sink must be visible to work queued on the default stream right after `backward()` - an all-reduce or an
+    optimiser step (functional._sink_written makes the default stream wait)."""
+    import neuradar_b200 as nb
+    from neuradar_b200 import functional as Fn
+    from neuradar_b200.dist import GradArena
+
+    spec = nb.HashEncoding(num_levels=16, features_per_level=2, log2_hashmap_size=17, min_res=16, max_res=1024).spec
+    g = torch.Generator().manual_seed(3)
+    M = 1 << 20  # ~1 ms of scatter: long enough for a missing dependency to show
+    x = torch.rand((M, 3), generator=g).to(DEV)
+    dy = torch.randn((M, 32), generator=g).to(DEV)
+    table = torch.nn.Parameter((torch.rand((spec.rows, 2), generator=g) * 2e-4 - 1e-4).to(DEV))
+    # expected: ordinary autograd accumulation on the default stream
+    (Fn.hash_encode(x, table, spec) * dy).sum().backward()
+    want = table.grad.clone()
+    table.grad = None
+    arena = GradArena([table], direct_scatter=True)
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        arena.zero()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            loss = (Fn.hash_encode(x, table, spec) * dy).sum()
+        torch.cuda.current_stream().wait_stream(side)
+        loss.backward()
+        got = arena.flat[: want.numel()].clone()  # queued on the default stream immediately after backward()
+        assert rel_err(got.view_as(want), want) <= 1e-5
