@@ -160,10 +160,12 @@ class ProposalNetworkSampler(Sampler):
         self._steps_since_update = 0
         self._step = 0
 
-    overlap_backward = os.environ.get("NRB_OVERLAP_PROPOSALS", "0") != "0"
-    """Optional (default off): run the proposal rounds on a side stream so that autograd replays their backward
-    concurrently with the main field's.  Measured neutral on B200 (11.91 vs 11.97 ms/step): both are bound by the
-    same L2 reduction throughput."""
+    overlap_backward = os.environ.get("NRB_OVERLAP_PROPOSALS", "1") != "0"
+    """Training: the proposal rounds run on a side stream, so that autograd replays their backward (which depends only on
+    the losses on the proposal weights - the PDF sampler is not differentiated) concurrently with the field's backward.
+    The proposal scatter is bound by L2 reductions, the field's backward by tensor-core latency and instruction issue:
+    measured 4.95 -> 4.86 ms/step at config 2 (B200, CUDA graph).  A persistent proposal backward sized to leave room on
+    every SM was measured too and is slower (it needs its full occupancy): DESIGN.md section 4."""
 
     def _on_side_stream(self, fn, ray_samples):
         dev = ray_samples.frustums.starts.device
