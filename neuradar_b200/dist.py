@@ -11,6 +11,8 @@ overlaps with the proposal backward; only the small remainder (proposal table + 
 """
 from __future__ import annotations
 
+import os
+
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 import torch
@@ -50,16 +52,37 @@ class OverlappedReduce:
         self._work = None
         self._stream: Optional[torch.cuda.Stream] = None
         self.group = None
+        self._early = None
+
+    early_ctas = int(os.environ.get("NRB_EARLY_REDUCE_CTAS", "8"))
+    """CTAs NCCL may use for the EARLY collective.  It runs beside the proposal backward, which it slows down in proportion
+    to the SMs it occupies (B200 x8, 64 MiB: 16+ CTAs by default, 0.28 ms alone, +0.15 ms on the overlapped kernels;
+    8 CTAs: 0.50 ms alone, still well inside the 1.3 ms it has to hide in; profiles/r2_nccl_probe_n8.txt)."""
+
+    def _early_group(self):
+        """A second NCCL communicator over the same ranks whose kernels are limited to `early_ctas` CTAs."""
+        if self._early is None:
+            self._early = self.group
+            if self.early_ctas > 0 and self.flat.is_cuda and dist.get_backend(self.group) == "nccl" and self.group is None:
+                try:
+                    opts = dist.ProcessGroupNCCL.Options()
+                    opts.config.max_ctas = self.early_ctas
+                    opts.config.min_ctas = 1
+                    self._early = dist.new_group(backend="nccl", pg_options=opts)
+                except Exception:  # noqa: BLE001 - an older torch / NCCL without communicator configs: use the default one
+                    self._early = self.group
+        return self._early
 
     def start_early(self) -> None:
         if self.n_early <= 0 or self._work is not None or _world(self.group) == 1:
             return
         if self.flat.is_cuda:
+            group = self._early_group()
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=self.flat.device)
             self._stream.wait_stream(torch.cuda.current_stream(self.flat.device))
             with torch.cuda.stream(self._stream):
-                self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=group, async_op=True)
         else:
             self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 

@@ -131,6 +131,14 @@ class PDFSampler(Sampler):
         return _make_ray_samples(ray_bundle, rays, sbins, ebins, ray_samples.spacing, ray_samples.spacing_to_euclidean_fn)
 
 
+def _data_parallel() -> bool:
+    """Under data parallelism the backward stays serial: the all-reduce of the main table's gradient (dist.GradArena,
+    `early`) then hides behind the proposal backward, which is worth more than overlapping the two backward branches."""
+    import torch.distributed as dist
+
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
 class ProposalNetworkSampler(Sampler):
     """Proposal-network sampling loop (ray_samplers.py:623-666)."""
 
@@ -169,7 +177,7 @@ class ProposalNetworkSampler(Sampler):
 
     def _on_side_stream(self, fn, ray_samples):
         dev = ray_samples.frustums.starts.device
-        if not (self.overlap_backward and torch.is_grad_enabled() and dev.type == "cuda"):
+        if not (self.overlap_backward and torch.is_grad_enabled() and dev.type == "cuda") or _data_parallel():
             return fn()
         main = torch.cuda.current_stream(dev)
         side = F.side_stream(dev, 2)
