@@ -458,13 +458,16 @@ def run_b200(args, rank, world, local_rank):
     ms_e2e = timed(load_host, args.steps, True)
 
     # ---- per-kernel durations from CUDA events on the launching stream (separate eager pass: the events add launch gaps)
+    # (the two backward branches are serialised for this pass: overlapped kernels would time each other's contention)
     reps = max(3, min(args.steps, 10))
+    overlap, model.sampler.overlap_backward = model.sampler.overlap_backward, False
     _lib.TIMER = _lib.KernelTimer()
     for i in range(reps):
         load_resident(i)
         step()
     kernels = _lib.TIMER.summary()
     _lib.TIMER = None
+    model.sampler.overlap_backward = overlap
 
     peaks = load_peaks()
     total_rays = n * world
@@ -527,6 +530,8 @@ def run_b200(args, rank, world, local_rank):
                    "parallelism": (f"ray-sharded dp{world}, all-reduce of a {arena_bytes / 2**20:.0f} MiB gradient arena in two "
                                    "pieces (main table overlapped with the proposal backward)") if w.train else f"replicas x{world}",
                    "launch": graph_note,
+                   "backward": ("proposal and field backward on two streams" if w.train and model.sampler.overlap_backward and world == 1
+                                else "single stream"),
                    "l2": f"{n_batches} resident ray batches rotated; per-step working set (tables 64-512 MiB, saved images, gradient "
                          "arena, > 0.7 GB) exceeds the 126 MB L2; no explicit flush",
                    "optimizer": ("fused Adam (hash grids) + AdamW (MLPs) inside the step" if args.optimizer
