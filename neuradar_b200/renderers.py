@@ -4,8 +4,9 @@ FeatureRenderer       <- nerfstudio/model_components/renderers.py:59-90
 AccumulationRenderer  <- nerfstudio/model_components/renderers.py:322-350
 DepthRenderer         <- nerfstudio/model_components/renderers.py:353-418
 render_depth_simple   <- nerfstudio/models/neurad.py:721-728
-The weighted sums run in `weighted_sum_kernel` via nrb_alpha_composite's accumulate stage: weights are given, so the
-compositor is invoked on them through `accumulate_along_rays`.
+The weights are given, so the weighted sums go through `nerfacc_compat.accumulate_along_rays`, i.e. `nrb_accumulate_fwd/bwd`
+(`accumulate_fwd_kernel`, csrc/compositing.cu: one warp per ray).  On the model's own path the field, the weights and these
+sums are one fused node instead (`NeuRADField.render`, `functional.field_render`).
 """
 from __future__ import annotations
 
