@@ -60,9 +60,10 @@ class PowerSampler(Sampler):
         def spacing_fn(x):
             return (lam_1 / lam) * ((x * scaling / lam_1 + 1) ** lam - 1)
 
-        s_near, s_far = spacing_fn(nears), spacing_fn(fars)
-
         def spacing_to_euclidean_fn(x):  # utils/math.py:561-580 / ray_samplers.py:117-120, for foreign callers
+            # (evaluated on demand: the kernels carry (lambda, scaling) and the per-ray near / far themselves, so on the
+            #  path this closure is never called and its ~12 element-wise launches per step are not spent)
+            s_near, s_far = spacing_fn(nears), spacing_fn(fars)
             v = x * s_far + (1 - x) * s_near
             return (((v * lam / lam_1 + 1).clamp_min(1e-10) ** (1 / lam) - 1) * lam_1) / scaling
 
