@@ -229,6 +229,20 @@ int nrb_actor_scatter(const nrb_actor_grids_t* grids, float* const* dtables, con
 int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,
                   float* y, nrb_stream_t stream);
 
+/* ---- radar ray generation: Radars._generate_rays_from_fov (cameras/radars.py:268-357) for a list
+ * of scans in one launch.  Per radar pose r: radar_to_worlds [R,3,4] and the field-of-view grid min_azimuth / azimuth_step
+ * / min_elevation / elevation_step [R] (the reference's `min_*` and `radar_*_ray_divergence` buffers).  scan_indices
+ * [n_scans] selects poses; ray_offsets [n_scans + 1] are the prefix sums of the rays per scan, n_azimuths x n_elevations
+ * with n = len(torch.arange(min, max, step)) (host arithmetic on the static sensor description), rays azimuth-major.
+ * Outputs, one row per ray: origins / directions [N,3], pixel_area [N] = (azimuth_step / 5)(elevation_step / 5),
+ * directions_spher [N,2] = (azimuth, elevation), directions_norm [N], ray_scan [N] = the pose index of the ray
+ * (camera_indices / the index the reference gathers times and metadata with). */
+int nrb_radar_rays(const float* radar_to_worlds, const float* min_azimuth, const float* azimuth_step,
+                   const float* min_elevation, const float* elevation_step, const int64_t* scan_indices,
+                   const int64_t* ray_offsets, const int32_t* n_elevations, int32_t n_scans, int64_t total_rays,
+                   float* origins, float* directions, float* pixel_area, float* directions_spher,
+                   float* directions_norm, int64_t* ray_scan, nrb_stream_t stream);
+
 /* ---- degree-4 real spherical harmonics of (d+1)/2: SHEncoding.pytorch_fwd on get_normalized_directions
  * (encodings.py:797-805, utils/math.py:31-94, fields/base_field.py:136-142).  dirs [M,3] -> out [M,16]. */
 int nrb_sh16(const float* dirs, float* out, int64_t M, int32_t normalize_to_unit_cube, nrb_stream_t stream);

@@ -23,6 +23,7 @@ from .fields import (  # noqa: F401
 from .losses import distortion_loss, lossfun_distortion, zipnerf_interlevel_loss  # noqa: F401
 from .nff import LossSettings, NeuRadarHotPath, NeuRadarHotPathConfig, SamplingSettings, bench_loss, training_losses  # noqa: F401
 from .ray_samplers import PDFSampler, PowerSampler, ProposalNetworkSampler  # noqa: F401
+from .radars import generate_rays_from_fov  # noqa: F401
 from .rays import Frustums, GaussiansStd, RayBundle, RaySamples  # noqa: F401
 from .renderers import AccumulationRenderer, DepthRenderer, FeatureRenderer, render_depth_simple  # noqa: F401
 

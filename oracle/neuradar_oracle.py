@@ -735,3 +735,34 @@ def adam_step(p: Tensor, g: Tensor, m: Tensor, v: Tensor, step: int, lr: float, 
     bc1, bc2 = 1 - betas[0] ** step, 1 - betas[1] ** step
     denom = (v.sqrt() / math.sqrt(bc2)).add_(eps)
     p.addcdiv_(m, denom, value=-(lr / bc1))
+
+
+# ------------------------------------------------------------------------------------------------
+# radar ray generation
+# ------------------------------------------------------------------------------------------------
+def radar_rays(radar_to_worlds: Tensor, min_az: Tensor, max_az: Tensor, az_step: Tensor, min_el: Tensor, max_el: Tensor,
+               el_step: Tensor, scan_indices: Tensor) -> Dict[str, Tensor]:
+    """Radars._generate_rays_from_fov (nerfstudio/cameras/radars.py:268-357), scan by scan like the reference:
+    arange x arange meshgrid ("ij") of azimuth / elevation, spherical -> cartesian (:312-315), rotate + translate by the
+    scan's radar_to_world (cameras/lidars.py:507-519), subtract the origin, normalize_with_norm (camera_utils.py:596-610),
+    pixel_area = (azimuth_step / 5)(elevation_step / 5) (:322-328)."""
+    eps = torch.finfo(torch.float32).eps
+    spher, scans = [], []
+    for idx in scan_indices.tolist():
+        az = torch.arange(float(min_az[idx]), float(max_az[idx]), float(az_step[idx]))
+        el = torch.arange(float(min_el[idx]), float(max_el[idx]), float(el_step[idx]))
+        ga, ge = torch.meshgrid(az, el, indexing="ij")
+        spher.append(torch.stack((ga.flatten(), ge.flatten()), dim=1))
+        scans.append(torch.full((ga.numel(),), idx, dtype=torch.int64))
+    spher = torch.cat(spher) if spher else torch.zeros((0, 2))
+    scans = torch.cat(scans) if scans else torch.zeros((0,), dtype=torch.int64)
+    r2w = radar_to_worlds[scans]
+    origins = r2w[:, :3, 3]
+    d = torch.stack([torch.cos(spher[:, 1]) * torch.cos(spher[:, 0]), torch.cos(spher[:, 1]) * torch.sin(spher[:, 0]),
+                     torch.sin(spher[:, 1])], dim=-1)
+    p = (d.unsqueeze(-2) @ r2w[:, :3, :3].swapaxes(-2, -1)).squeeze(-2) + origins
+    v = p - origins
+    norm = torch.maximum(torch.linalg.vector_norm(v, dim=-1, keepdim=True), torch.tensor([eps]))
+    pixel_area = (az_step[scans] / 5) * (el_step[scans] / 5)
+    return {"origins": origins, "directions": v / norm, "pixel_area": pixel_area.reshape(-1, 1), "directions_spher": spher,
+            "directions_norm": norm, "ray_scan": scans}

@@ -470,7 +470,43 @@ def gen_losses():
     save("losses", **out)
 
 
+def gen_radar_rays():
+    """Radars._generate_rays_from_fov (cameras/radars.py:268-357) for poses with the default and with non-dyadic fields of
+    view."""
+    import math
+
+    from nerfstudio.cameras.radars import Radars
+
+    g = torch.Generator().manual_seed(17)
+    n = 6
+    yaw, pitch = torch.rand(n, generator=g) * 2 * math.pi, (torch.rand(n, generator=g) - 0.5) * 0.2
+    cy, sy, cp, sp = torch.cos(yaw), torch.sin(yaw), torch.cos(pitch), torch.sin(pitch)
+    z, o = torch.zeros(n), torch.ones(n)
+    Rz = torch.stack([torch.stack([cy, -sy, z], -1), torch.stack([sy, cy, z], -1), torch.stack([z, z, o], -1)], -2)
+    Ry = torch.stack([torch.stack([cp, z, sp], -1), torch.stack([z, o, z], -1), torch.stack([-sp, z, cp], -1)], -2)
+    t = (torch.rand((n, 3, 1), generator=g) - 0.5) * torch.tensor([200.0, 200.0, 4.0]).reshape(1, 3, 1)
+    r2w = torch.cat([Rz @ Ry, t], -1)
+    fov = dict(radar_azimuth_ray_divergence=torch.tensor([0.0625, 0.0625, 0.05, 0.03, 0.0625, 0.11]).reshape(n, 1),
+               radar_elevation_ray_divergence=torch.tensor([0.0625, 0.0625, 0.07, 0.0625, 0.02, 0.13]).reshape(n, 1),
+               min_azimuth=torch.tensor([-0.5, -0.5, -0.6, -0.31, -0.5, -0.9]).reshape(n, 1),
+               max_azimuth=torch.tensor([0.5, 0.5, 0.55, 0.33, 0.5, 0.85]).reshape(n, 1),
+               min_elevation=torch.tensor([-0.5, -0.5, -0.2, -0.5, -0.11, -0.3]).reshape(n, 1),
+               max_elevation=torch.tensor([0.5, 0.5, 0.27, 0.5, 0.12, 0.35]).reshape(n, 1))
+    radars = Radars(radar_to_worlds=r2w, times=torch.arange(n).float() * 0.1, **fov)
+    scans = torch.tensor([4, 0, 5, 2, 2, 3])
+    rb = radars._generate_rays_from_fov(scans)
+    out = dict(radar_to_worlds=r2w, scan_indices=scans, times_in=radars.times, **fov)
+    out.update(origins=rb.origins, directions=rb.directions, pixel_area=rb.pixel_area, camera_indices=rb.camera_indices,
+               times=rb.times, fars=rb.fars, directions_norm=rb.metadata["directions_norm"],
+               did_return=rb.metadata["did_return"], directions_spher=rb.metadata["directions_spher"])
+    print("radar rays:", rb.origins.shape[0])
+    save("radar_rays", **out)
+
+
 if __name__ == "__main__":
+    if "--radar-rays-only" in sys.argv:
+        gen_radar_rays()
+        sys.exit(0)
     if "--losses-only" in sys.argv:
         gen_losses()
     elif "--actors-only" in sys.argv:
@@ -479,3 +515,4 @@ if __name__ == "__main__":
         _main_all()
         gen_actors()
         gen_losses()
+        gen_radar_rays()

@@ -293,3 +293,18 @@ def test_is_close_to_lidar_matches_reference_method():
         got = O.is_close_to_lidar(bins[:, :-1], bins[:, 1:], is_lidar, dnorm, did_return if use_return else None)
         assert torch.equal(got, want)
         assert bool(want.any()) and not bool(want.all())
+
+
+def test_radar_rays(golden):
+    """Radar ray generation against Radars._generate_rays_from_fov of the reference."""
+    g = golden("radar_rays")
+    out = O.radar_rays(g["radar_to_worlds"], g["min_azimuth"].reshape(-1), g["max_azimuth"].reshape(-1),
+                       g["radar_azimuth_ray_divergence"].reshape(-1), g["min_elevation"].reshape(-1),
+                       g["max_elevation"].reshape(-1), g["radar_elevation_ray_divergence"].reshape(-1), g["scan_indices"])
+    assert torch.equal(out["ray_scan"], g["camera_indices"][:, 0])
+    assert torch.equal(out["origins"], g["origins"])
+    assert torch.equal(out["directions_spher"], g["directions_spher"])
+    assert torch.equal(out["pixel_area"], g["pixel_area"])
+    assert float((out["directions"] - g["directions"]).abs().max()) <= 1e-7
+    assert float((out["directions_norm"] - g["directions_norm"]).abs().max()) <= 1e-7
+    assert out["directions"].shape[0] == 1232  # six scans with ragged fields of view (two of them the default 16 x 16)
