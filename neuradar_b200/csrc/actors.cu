@@ -26,9 +26,42 @@ __global__ void __launch_bounds__(256) actor_assign_kernel(const float* __restri
                                                            float* __restrict__ pos, float* __restrict__ std,
                                                            float* __restrict__ dirs, int32_t* __restrict__ actor_index,
                                                            int64_t total) {
-  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= total) return;
+  // Per-ray pre-cull (the reference's own first filter, neurad_encoding.py:231-247): an actor can only claim samples of
+  // a ray whose line passes its bounding sphere.  The block's 256 consecutive samples belong to a handful of rays; the
+  // first threads test every (ray, actor) pair once and leave a bit mask per ray, the per-sample loop below then runs
+  // the exact box test only for the flagged actors (typically none or one of 16).  The sphere contains the box, and the
+  // test is evaluated with a margin, so the result is the plain loop's.
+  constexpr int kCullRays = 8;
+  __shared__ uint32_t s_mask[kCullRays];
   const int S = iv.num_samples;
+  const int64_t first = static_cast<int64_t>(blockIdx.x) * blockDim.x;
+  const int64_t last = min(first + blockDim.x, total) - 1;
+  const int64_t n0 = first / S;
+  const int nrays = static_cast<int>(last / S - n0) + 1;
+  const bool cull = nrays <= kCullRays && A <= 32;
+  if (cull) {
+    if (threadIdx.x < kCullRays) s_mask[threadIdx.x] = 0u;
+    __syncthreads();
+    for (int p = threadIdx.x; p < nrays * A; p += blockDim.x) {
+      const int64_t n = n0 + p / A;
+      const int a = p % A;
+      if (!valid[n * A + a]) continue;
+      const float* m = world2boxes + (n * A + a) * 12;
+      const float ox = origins[3 * n], oy = origins[3 * n + 1], oz = origins[3 * n + 2];
+      const float dx = directions[3 * n], dy = directions[3 * n + 1], dz = directions[3 * n + 2];
+      const float px = m[0] * ox + m[1] * oy + m[2] * oz + m[3], py = m[4] * ox + m[5] * oy + m[6] * oz + m[7],
+                  pz = m[8] * ox + m[9] * oy + m[10] * oz + m[11];
+      const float qx = m[0] * dx + m[1] * dy + m[2] * dz, qy = m[4] * dx + m[5] * dy + m[6] * dz,
+                  qz = m[8] * dx + m[9] * dy + m[10] * dz;
+      const float cx = py * qz - pz * qy, cy = pz * qx - px * qz, cz = px * qy - py * qx;  // |p x q| = distance * |q|
+      const float r2 = bounds[3 * a] * bounds[3 * a] + bounds[3 * a + 1] * bounds[3 * a + 1] + bounds[3 * a + 2] * bounds[3 * a + 2];
+      if (cx * cx + cy * cy + cz * cz <= (r2 * 1.01f + 1.0e-6f) * (qx * qx + qy * qy + qz * qz))
+        atomicOr(&s_mask[p / A], 1u << a);
+    }
+    __syncthreads();
+  }
+  const int64_t gid = first + threadIdx.x;
+  if (gid >= total) return;
   const int64_t n = gid / S;
   const int s = static_cast<int>(gid - n * S);
   const float dx = directions[3 * n], dy = directions[3 * n + 1], dz = directions[3 * n + 2];
@@ -36,15 +69,23 @@ __global__ void __launch_bounds__(256) actor_assign_kernel(const float* __restri
                                     iv.starts[n * iv.row_stride + s], iv.ends[n * iv.row_stride + s]);
   int hit = -1;
   float bx = 0.f, by = 0.f, bz = 0.f;
-  for (int a = 0; a < A; ++a) {
-    if (!valid[n * A + a]) continue;
-    const float* m = world2boxes + (n * A + a) * 12;
-    const float x = m[0] * w.x + m[1] * w.y + m[2] * w.z + m[3];
-    const float y = m[4] * w.x + m[5] * w.y + m[6] * w.z + m[7];
-    const float z = m[8] * w.x + m[9] * w.y + m[10] * w.z + m[11];
-    if (fabsf(x) < bounds[3 * a] && fabsf(y) < bounds[3 * a + 1] && fabsf(z) < bounds[3 * a + 2]) {
-      hit = a;
-      bx = x, by = y, bz = z;
+  uint32_t todo = cull ? s_mask[n - n0] : (A >= 32 ? 0xFFFFFFFFu : (1u << A) - 1u);
+  for (int a0 = 0; a0 < A; a0 += 32) {  // (more than 32 actors: plain loop in chunks of 32)
+    uint32_t bits = a0 == 0 ? todo : 0xFFFFFFFFu;
+    while (bits != 0u) {
+      const int a = a0 + __ffs(bits) - 1;
+      bits &= bits - 1u;
+      if (a >= A) break;
+      if (!valid[n * A + a]) continue;
+      const float* m = world2boxes + (n * A + a) * 12;
+      // rotation as a dot product, then the translation (transform_points_pairwise, cameras/lidars.py:507-519)
+      const float x = add(fmaf(m[2], w.z, fmaf(m[1], w.y, mul(m[0], w.x))), m[3]);
+      const float y = add(fmaf(m[6], w.z, fmaf(m[5], w.y, mul(m[4], w.x))), m[7]);
+      const float z = add(fmaf(m[10], w.z, fmaf(m[9], w.y, mul(m[8], w.x))), m[11]);
+      if (fabsf(x) < bounds[3 * a] && fabsf(y) < bounds[3 * a + 1] && fabsf(z) < bounds[3 * a + 2]) {
+        hit = a;
+        bx = x, by = y, bz = z;
+      }
     }
   }
   grid_id[gid] = hit >= 0 ? actor_to_id[hit] : -1;

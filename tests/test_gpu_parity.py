@@ -714,7 +714,9 @@ def test_actor_path_has_no_host_sync(nb):
     feats_kernel = fld(rs)[nb.FieldHeadNames.FEATURE]
     fld.hashgrid.can_assign_in_kernel = lambda proposal=False: False
     feats_torch = fld(rs)[nb.FieldHeadNames.FEATURE]
-    assert rel_err(feats_kernel, feats_torch) <= 1e-5
+    # (box-frame positions differ by an ulp between the torch path's matmul and the kernel's fused multiply-adds; the
+    #  finest actor level multiplies that by its resolution)
+    assert rel_err(feats_kernel, feats_torch) <= 3e-5
 
 
 def test_proposal_round_with_actors_matches_torch_bookkeeping(nb):
@@ -768,7 +770,7 @@ def test_proposal_round_with_actors_matches_torch_bookkeeping(nb):
     assert inside > 100, inside
     prop.hashgrid.can_assign_in_kernel = lambda proposal=False: False
     dens_t, w_t, grads_t = run()
-    assert rel_err(dens_k, dens_t) <= 1e-5 and rel_err(w_k, w_t) <= 1e-5
+    assert rel_err(dens_k, dens_t) <= 3e-5 and rel_err(w_k, w_t) <= 3e-5
     assert set(grads_k) == set(grads_t)
     nonzero_actor_tables = 0
     for k in grads_t:
