@@ -341,10 +341,27 @@ def run_b200(args, rank, world, local_rank):
     keys = ["origins", "directions", "pixel_area", "nears", "fars", "times", "is_lidar", "is_radar"]
     n_batches = N_BATCHES if n <= (1 << 17) else 1
     batches_cpu = [synthetic_rays(n, seed=42 + rank + 1000 * b, mix=w.mix) for b in range(n_batches)]
-    host = [{k: b[k].pin_memory() for k in keys} for b in batches_cpu]
-    resident = [{k: b[k].to(dev) for k in keys} for b in batches_cpu]
-    cur = {k: torch.empty_like(resident[0][k]) for k in keys}  # the step's (static) inputs
-    h2d_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in keys)
+    # one flat byte buffer per batch (fields at 256-byte aligned offsets): a step's rays move host -> device in ONE copy
+    offsets, total_bytes = {}, 0
+    for k in keys:
+        offsets[k] = total_bytes
+        total_bytes += (batches_cpu[0][k].numel() * batches_cpu[0][k].element_size() + 255) // 256 * 256
+
+    def views(flat):
+        return {k: flat[offsets[k]: offsets[k] + batches_cpu[0][k].numel() * batches_cpu[0][k].element_size()]
+                .view(batches_cpu[0][k].dtype).view(batches_cpu[0][k].shape) for k in keys}
+
+    host_flat = [torch.zeros((total_bytes,), dtype=torch.uint8).pin_memory() for _ in batches_cpu]
+    for hf, b in zip(host_flat, batches_cpu):
+        for k, v in views(hf).items():
+            v.copy_(b[k])
+    resident_flat = [hf.to(dev) for hf in host_flat]
+    cur_flat = torch.empty((total_bytes,), dtype=torch.uint8, device=dev)
+    cur = views(cur_flat)  # the step's (static) inputs
+    staging = [torch.empty_like(cur_flat) for _ in range(2)]  # landing buffers of the prefetching host -> device copies
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    h2d_bytes = sum(batches_cpu[0][k].numel() * batches_cpu[0][k].element_size() for k in keys)
 
     def bundle(src, lo=0, hi=None):
         sl = slice(lo, hi)
@@ -381,12 +398,18 @@ def run_b200(args, rank, world, local_rank):
         result["loss"] = loss.detach()
 
     def load_resident(i):
-        for k in keys:
-            cur[k].copy_(resident[i % n_batches][k], non_blocking=True)
+        cur_flat.copy_(resident_flat[i % n_batches], non_blocking=True)
+
+    def prefetch_host(i):
+        """Host -> device copy of step i's rays (pinned memory) on the copy stream, into staging buffer i % 2."""
+        with torch.cuda.stream(copy_stream):
+            staging[i % 2].copy_(host_flat[i % n_batches], non_blocking=True)
+            copied[i % 2].record(copy_stream)
 
     def load_host(i):
-        for k in keys:
-            cur[k].copy_(host[i % n_batches][k], non_blocking=True)
+        """Step i's rays are on their way (prefetch_host(i)); the step waits for them and takes them over."""
+        torch.cuda.current_stream(dev).wait_event(copied[i % 2])
+        cur_flat.copy_(staging[i % 2], non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -430,13 +453,20 @@ def run_b200(args, rank, world, local_rank):
             step()
 
     def timed(loader, steps, read_back):
+        """read_back=False: rays resident in HBM.  read_back=True: the end-to-end loop of a training process with a
+        prefetching loader - every step's rays are copied from pinned host memory inside the timed region (the copy of
+        step i+1 is in flight while step i computes, like a data loader's prefetch), every step's loss is read back."""
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if read_back:
+            prefetch_host(0)
         for i in range(steps):
             loader(i)
             run_step()
             if read_back:
+                if i + 1 < steps:
+                    prefetch_host(i + 1)
                 result["loss"].item()  # device -> host read of the step's result
         e1.record()
         barrier()
@@ -453,8 +483,10 @@ def run_b200(args, rank, world, local_rank):
         ms = timed(load_resident, args.steps, False)
     launches = _lib.launch_count() - l0 if graph is None else launches_per_step * args.steps
     for i in range(2):
+        prefetch_host(i)
         load_host(i)
         run_step()
+    torch.cuda.synchronize()
     ms_e2e = timed(load_host, args.steps, True)
 
     # ---- per-kernel durations from CUDA events on the launching stream (separate eager pass: the events add launch gaps)
@@ -538,7 +570,9 @@ def run_b200(args, rank, world, local_rank):
                                  else "not part of the path (SURVEY.md 8f next-2; --optimizer adds it)") if w.train else "n/a",
                    "regularisers": bool(args.regularisers)},
         "e2e": {"value": total_rays / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
+                "note": "per step: one pinned host -> device copy of the rays (prefetched on a copy stream while the previous step "
+                        "computes, as a data loader does), the step, loss.item()"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roofline,
