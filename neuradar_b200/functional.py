@@ -119,7 +119,10 @@ class SampleIntervals:
         if not self.starts.is_cuda:
             raise _lib.NeuradarB200Error("neuradar_b200 ops need CUDA tensors; there is no CPU path")
         iv = Intervals()
-        iv.starts, iv.ends = self.starts.data_ptr(), self.ends.data_ptr()
+        # (views of a bins tensor are not contiguous, so no ptr(); empty tensors have a null data_ptr: see _lib.ptr)
+        empty = self.starts.numel() == 0
+        iv.starts = _lib._EMPTY_SENTINEL if empty else self.starts.data_ptr()
+        iv.ends = _lib._EMPTY_SENTINEL if empty else self.ends.data_ptr()
         iv.row_stride = self.starts.stride(0) if self.starts.shape[0] > 1 else max(self.starts.stride(0), self.num_samples)
         iv.num_samples = self.num_samples
         return iv

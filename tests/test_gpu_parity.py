@@ -460,6 +460,30 @@ def test_whole_path_vs_oracle(nb, train):
     assert report["ok"], report
 
 
+@pytest.mark.parametrize("num_rays", [1, 3, 131])
+def test_whole_path_ragged_ray_counts_vs_oracle(nb, num_rays):
+    """Ray counts that leave every kernel with a partial last tile / warp / block (a single ray: 48 samples in a 128-sample
+    tile; 131 rays: 6288 samples = 49 tiles + 16 rows)."""
+    report = run_path_parity(num_rays=num_rays, device=DEV, seed=5 + num_rays, train=True)
+    assert report["ok"], report
+
+
+def test_whole_path_zero_rays(nb):
+    """An empty batch (a rank whose shard is empty, the tail chunk of an inference sweep) passes through every kernel
+    entry point without a launch and yields empty outputs of the right shapes, forward and backward."""
+    model = build_hot_path(log2_main=10, log2_prop=10, device=DEV)
+    model.train()
+    rays = synthetic_rays(4, seed=1)
+    rb = make_ray_bundle({k: v[:0] for k, v in rays.items()}, DEV)
+    out = model(rb)
+    assert out["features"].shape == (0, 32) and out["depth"].shape == (0, 1) and out["accumulation"].shape == (0, 1)
+    assert [w.shape for w in out["weights_list"]] == [(0, 64, 1), (0, 48, 1), (0, 47, 1)]  # (the sky sample is dropped)
+    loss = out["features"].sum() + out["depth"].sum() + sum(w.sum() for w in out["weights_list"])
+    loss.backward()
+    for name, p in model.named_parameters():
+        assert p.grad is None or float(p.grad.abs().sum()) == 0.0, name
+
+
 def test_whole_path_with_regularisers_vs_oracle(nb):
     """The step as the model trains it: path + interlevel + distortion losses, gradients of every parameter."""
     report = run_path_parity(num_rays=384, device=DEV, seed=17, train=True, with_losses=True)
