@@ -436,6 +436,55 @@ def test_proposal_round_vs_oracle(nb):
     assert rel_err(rs.get_weights(d2), w_ref) <= 1e-4
 
 
+def test_maximum_samples_per_ray(nb):
+    """NRB_MAX_SAMPLES = 256 samples per ray is the most the warp-per-ray kernels hold (8 chunks of 32 lanes): 256 must agree
+    with the oracle (proposal round, PDF sampling, compositing), 257 must be refused with an error, not truncated."""
+    import neuradar_b200 as pkg
+    from neuradar_b200 import functional as Fn
+
+    N, S = 96, 256
+    model = build_hot_path(log2_main=12, log2_prop=13, table_gain=(300.0, 2000.0), seed=4, device=DEV)
+    rays = synthetic_rays(N, seed=16)
+    pa = scaled_pixel_area(rays)
+    g = torch.Generator().manual_seed(2)
+    sb, eb, _ = O.spaced_bins(rays["nears"], rays["fars"].clamp_max(20000.0), S, torch.rand((N, S + 1), generator=g))
+    eb = eb.contiguous()
+    _, props = oracle_params(model)
+    dens_ref = O.proposal_density(props[1], rays["origins"], rays["directions"], pa, eb[:, :-1], eb[:, 1:])
+    w_ref = O.density_weights(dens_ref, (eb[:, 1:] - eb[:, :-1])[..., None])
+    rd = Fn.RayData(rays["origins"].to(DEV), rays["directions"].to(DEV), pa.to(DEV), rays["nears"].to(DEV),
+                    rays["fars"].clamp_max(20000.0).to(DEV))
+    pf = model.proposal_fields[1]
+    dens, w = Fn.proposal_round(pf.hashgrid.static_grid.hash_table, pf.density_decoder.weight, rd,
+                                Fn.SampleIntervals.from_bins(eb.to(DEV)), pf.hashgrid.static_grid.spec, 100.0)
+    assert rel_err(dens, dens_ref[..., 0]) <= 1e-4 and rel_err(w, w_ref[..., 0]) <= 1e-4
+    (w * w).sum().backward()
+    (w_ref * w_ref).sum().backward()
+    assert rel_err(pf.hashgrid.static_grid.hash_table.grad, props[1].grid.table.grad) <= 1e-3
+    # PDF sampling from 256 input bins into 256 output bins
+    j1 = torch.rand((N, 1), generator=g)
+    sb1, eb1, inds, cdf = Fn.pdf_sample(rd, w.detach(), sb.to(DEV), S, j1.to(DEV), -1.0, 0.1, return_debug=True)
+    u = O.pdf_u(N, S, j1)
+    assert torch.equal(inds.cpu(), torch.searchsorted(cdf.cpu().contiguous(), u, side="right"))
+    assert float((cdf.cpu() - O.pdf_cdf(w.detach().cpu())).abs().max()) <= 5e-7
+    assert bool((sb1[:, 1:] >= sb1[:, :-1]).all())
+    # compositing of 256 samples
+    alpha = torch.rand((N, S), generator=g) * 0.05
+    feats = torch.randn((N, S, 32), generator=g)
+    wts, feat, depth, acc = Fn.alpha_composite(alpha.to(DEV), feats.to(DEV), Fn.SampleIntervals.from_bins(eb.to(DEV)),
+                                               trans_eps=0.0, sky_sample=True)
+    ref_w, _ = O.alpha_weights(alpha, eps=0.0)
+    assert rel_err(wts[:, :-1], ref_w[:, :-1]) <= 1e-5
+    # one sample more than the kernels hold: refused
+    eb257 = torch.cat([eb, eb[:, -1:] + 1.0], dim=-1).to(DEV)
+    with pytest.raises(pkg._lib.NeuradarB200Error):
+        Fn.proposal_round(pf.hashgrid.static_grid.hash_table, pf.density_decoder.weight, rd,
+                          Fn.SampleIntervals.from_bins(eb257), pf.hashgrid.static_grid.spec, 100.0)
+    with pytest.raises(pkg._lib.NeuradarB200Error):
+        Fn.alpha_composite(torch.rand((N, S + 1), device=DEV), torch.randn((N, S + 1, 32), device=DEV),
+                           Fn.SampleIntervals.from_bins(eb257), trans_eps=0.0, sky_sample=True)
+
+
 def test_field_forward_vs_oracle(nb):
     model = build_hot_path(log2_main=14, log2_prop=12, table_gain=(300.0, 2000.0), seed=9, device=DEV)
     rays = synthetic_rays(320, seed=10)
