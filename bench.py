@@ -560,7 +560,7 @@ def run_b200(args, rank, world, local_rank):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": w.description, "rays_per_gpu": n, "global_rays": total_rays,
                    "parallelism": (f"ray-sharded dp{world}, all-reduce of a {arena_bytes / 2**20:.0f} MiB gradient arena in two "
-                                   "pieces (main table overlapped with the proposal backward)") if w.train else f"replicas x{world}",
+                                   "pieces (main table overlapped with the proposal backward); see `collective`") if w.train else f"replicas x{world}",
                    "launch": graph_note,
                    "backward": ("proposal and field backward on two streams" if w.train and model.sampler.overlap_backward and world == 1
                                 else "single stream"),
@@ -583,6 +583,28 @@ def run_b200(args, rank, world, local_rank):
         "kernels": per_step,
         "kernel_ms_per_step": kernel_ms,
     }
+    if world > 1 and arena is not None:
+        # the exchange step against NCCL on the same data: fill the arena with a per-rank pattern, reduce it the way the
+        # step does (early piece + tail), compare with NCCL's all-reduce of a copy
+        gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+        pattern = torch.randn((arena.flat.numel(),), device=dev, generator=gen)
+        want = pattern.clone()
+        dist.all_reduce(want)
+        want /= world
+        arena.flat.copy_(pattern)
+        torch.cuda.synchronize()
+        dist.barrier()
+        arena.reducer.start_early()
+        arena.all_reduce()
+        torch.cuda.synchronize()
+        diff = (arena.flat - want).abs().max()
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        kind = "NCCL all-reduce (two communicators)"
+        if arena.peer is not None:
+            kind = ("own kernel over NVLink peer memory, " +
+                    ("in-switch reduction (NVLS multimem)" if arena.peer.multicast_ptr else "unicast two-shot") + ", x 1/world fused")
+        line["collective"] = {"kind": kind, "bytes": arena.nbytes, "early_bytes": arena.reducer.n_early * 4,
+                              "max_abs_diff_vs_nccl": float(diff)}
     if w.actors:  # how many field samples the actor boxes claimed on this batch (bytes_per_ray assumes ~10 %)
         with torch.no_grad():
             rs = model(bundle(cur))["ray_samples_list"][-1]

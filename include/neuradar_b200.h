@@ -229,6 +229,19 @@ int nrb_actor_scatter(const nrb_actor_grids_t* grids, float* const* dtables, con
 int nrb_tc_linear(const float* x, const float* w, const float* b, int32_t K, int32_t n_out, int32_t relu, int64_t M,
                   float* y, nrb_stream_t stream);
 
+/* ---- all-reduce of the gradient arena over NVLink peer memory: DistributedDataParallel's gradient
+ * average (pipelines/base_pipeline.py:305-307) as one kernel per rank.  buffer_ptrs[p] / signal_flag_ptrs[p] (host arrays
+ * of `world` device addresses): rank p's arena and a 1 KB zero-initialised flag area, both mapped into this process
+ * (symmetric memory).  In place over floats [offset, offset + n) of every arena: sum over ranks, times `scale`.  Two-shot:
+ * each rank reduces its 1/world slice from all arenas and writes the result to all arenas; epoch-stamped flags at system
+ * scope order the phases, so the call can be captured in a CUDA graph.  `slot` (0..3) selects an independent flag set
+ * (collectives that may be in flight together need different slots); `max_ctas` bounds the SMs the kernel occupies
+ * (0: no bound).  multicast_ptr (0: none): the arenas bound to one NVLS multicast object - the reduction then happens in
+ * the switch (multimem.ld_reduce / multimem.st), which moves half the bytes.  All ranks must call with the same arguments
+ * but `rank`. */
+int nrb_peer_all_reduce(const uint64_t* buffer_ptrs, const uint64_t* signal_flag_ptrs, uint64_t multicast_ptr,
+                        int32_t rank, int32_t world, int32_t slot, int64_t offset, int64_t n, float scale, int32_t max_ctas, nrb_stream_t stream);
+
 /* ---- radar ray generation: Radars._generate_rays_from_fov (cameras/radars.py:268-357) for a list
  * of scans in one launch.  Per radar pose r: radar_to_worlds [R,3,4] and the field-of-view grid min_azimuth / azimuth_step
  * / min_elevation / elevation_step [R] (the reference's `min_*` and `radar_*_ray_divergence` buffers).  scan_indices

@@ -40,6 +40,65 @@ def _world(group=None) -> int:
     return dist.get_world_size(group)
 
 
+class PeerMemory:
+    """A flat fp32 buffer in symmetric memory (every rank's copy is mapped into every process of the box) plus a zeroed
+    flag area, for `nrb_peer_all_reduce` (csrc/peer_reduce.cu).  Built on torch.distributed._symmetric_memory, which only
+    provides the mapping; the collective is this package's kernel."""
+
+    def __init__(self, numel: int, device, group=None):
+        import ctypes as C
+
+        import torch.distributed._symmetric_memory as symm
+
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        pg = group if group is not None else dist.group.WORLD
+        self.flat = symm.empty(numel, dtype=torch.float32, device=device)
+        self.flags = symm.empty(256, dtype=torch.int32, device=device)  # 4 slots x 64 words (peer_reduce.cu: kSlotWords)
+        self.flat.zero_()
+        self.flags.zero_()
+        h_flat, h_flags = symm.rendezvous(self.flat, pg), symm.rendezvous(self.flags, pg)
+        bufs = [h_flat.get_buffer(p, (numel,), torch.float32).data_ptr() for p in range(self.world)]
+        sigs = [h_flags.get_buffer(p, (256,), torch.int32).data_ptr() for p in range(self.world)]
+        self._handles = (h_flat, h_flags)
+        # NVLS: the W replicas of the arena behind one multicast address, when the fabric offers it (NRB_PEER_MULTICAST=0: no)
+        self.multicast_ptr = 0
+        if os.environ.get("NRB_PEER_MULTICAST", "1") != "0":
+            try:
+                # (with two ranks the switch has nothing to save; measured slower than the unicast form)
+                base = int(h_flat.multicast_ptr or 0) if self.world > 2 else 0
+                self.multicast_ptr = base + int(getattr(h_flat, "offset", 0)) if base else 0
+            except Exception:  # noqa: BLE001
+                self.multicast_ptr = 0
+        self.buffer_ptrs = (C.c_uint64 * self.world)(*bufs)
+        self.flag_ptrs = (C.c_uint64 * self.world)(*sigs)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)  # every rank's flags are zero before anyone's first collective
+
+    def all_reduce(self, slot: int, offset: int, n: int, scale: float, max_ctas: int = 0) -> None:
+        """In place over floats [offset, offset + n) of every rank's buffer, on the current stream."""
+        from . import _lib
+
+        _lib.call("nrb_peer_all_reduce", self.buffer_ptrs, self.flag_ptrs, self.multicast_ptr, self.rank, self.world, slot, offset,
+                  n, float(scale), max_ctas, _lib.stream_ptr())
+
+
+def peer_memory_or_none(numel: int, device, group=None) -> Optional[PeerMemory]:
+    """Symmetric memory for the arena when this is a single-box NCCL job of at most 8 ranks (NRB_PEER_REDUCE=0 disables)."""
+    if os.environ.get("NRB_PEER_REDUCE", "1") == "0" or _world(group) == 1 or torch.device(device).type != "cuda":
+        return None
+    if dist.get_backend(group) != "nccl" or dist.get_world_size(group) > 8 or group is not None:
+        return None
+    if int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size())) != dist.get_world_size():
+        return None  # more than one box: the ranks do not share an NVSwitch domain
+    try:
+        return PeerMemory(numel, device, group)
+    except Exception as e:  # noqa: BLE001 - no peer mapping on this system: NCCL carries the collective
+        import warnings
+
+        warnings.warn(f"neuradar_b200: peer-memory all-reduce unavailable ({type(e).__name__}: {str(e)[:120]}); using NCCL")
+        return None
+
+
 class OverlappedReduce:
     """All-reduce of one flat gradient buffer whose first `n_early` elements become final early in the backward pass.
 
@@ -47,8 +106,9 @@ class OverlappedReduce:
     their all-reduce on a side stream; `finish()` reduces the rest and joins.  Without an early call `finish()` reduces
     everything in one collective.  Single process: no-ops."""
 
-    def __init__(self, flat: Tensor, n_early: int = 0):
+    def __init__(self, flat: Tensor, n_early: int = 0, peer: Optional[PeerMemory] = None):
         self.flat, self.n_early = flat, int(n_early)
+        self.peer = peer  # the arena lives in symmetric memory: this package's NVLink kernel instead of NCCL
         self._work = None
         self._stream: Optional[torch.cuda.Stream] = None
         self.group = None
@@ -73,23 +133,50 @@ class OverlappedReduce:
                     self._early = self.group
         return self._early
 
+    peer_ctas = int(os.environ.get("NRB_PEER_CTAS", "0"))
+    """CTAs of the peer-memory kernel (0 = measured defaults, profiles/r2_peer_reduce_probe.txt): with in-switch reduction
+    (NVLS multicast) 8 CTAs already saturate the links (8 x B200: 24 MiB in 71 us, 64 MiB in 159 us; more CTAs are slower);
+    without it the early piece gets 16 CTAs and the exposed tail all of them."""
+
+    def _peer_ctas(self, early: bool) -> int:
+        if self.peer_ctas > 0:
+            return self.peer_ctas
+        if self.peer.multicast_ptr:
+            return 8
+        return 16 if early else 0
+
     def start_early(self) -> None:
         if self.n_early <= 0 or self._work is not None or _world(self.group) == 1:
             return
         if self.flat.is_cuda:
-            group = self._early_group()
             if self._stream is None:
                 self._stream = torch.cuda.Stream(device=self.flat.device)
             self._stream.wait_stream(torch.cuda.current_stream(self.flat.device))
+            if self.peer is not None:
+                with torch.cuda.stream(self._stream):  # (already averaged: finish() returns 1)
+                    self.peer.all_reduce(0, 0, self.n_early, 1.0 / self.peer.world, self._peer_ctas(True))
+                self._work = True
+                return
+            group = self._early_group()
             with torch.cuda.stream(self._stream):
                 self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=group, async_op=True)
         else:
             self._work = dist.all_reduce(self.flat[: self.n_early], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def finish(self, group=None) -> float:
-        """Sum over ranks; returns 1 / world_size (the caller applies the average or hands it to the optimiser)."""
+        """Sum over ranks; returns the factor that still has to be applied for the average: 1 / world_size after NCCL (the
+        caller applies it or hands it to the optimiser), 1 after the peer-memory kernel (which averages in place)."""
         world = _world(group)
         if world == 1:
+            return 1.0
+        if self.peer is not None:  # sums AND averages in place (the x 1/world rides in the kernel)
+            total = self.flat.numel()
+            if self._work is not None:
+                self.peer.all_reduce(1, self.n_early, total - self.n_early, 1.0 / world, self._peer_ctas(False))
+                torch.cuda.current_stream(self.flat.device).wait_stream(self._stream)
+                self._work = None
+            else:
+                self.peer.all_reduce(1, 0, total, 1.0 / world, self._peer_ctas(False))
             return 1.0
         if self._work is not None:
             dist.all_reduce(self.flat[self.n_early :], op=dist.ReduceOp.SUM, group=group)
@@ -140,9 +227,10 @@ class GradArena:
             total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned for the vector atomics
             if i < n_first:
                 n_early = total
-        self.flat = torch.zeros((total,), device=dev, dtype=torch.float32)
+        self.peer = peer_memory_or_none(total, dev)
+        self.flat = self.peer.flat if self.peer is not None else torch.zeros((total,), device=dev, dtype=torch.float32)
         self.direct_scatter = direct_scatter
-        self.reducer = OverlappedReduce(self.flat, n_early)
+        self.reducer = OverlappedReduce(self.flat, n_early, self.peer)
         self._views = [self.flat[off : off + p.numel()].view_as(p) for p, off in zip(self.params, self.offsets)]
         for i, (p, view) in enumerate(zip(self.params, self._views)):
             p.grad = view
@@ -180,3 +268,5 @@ class GradArena:
         mult = self.reducer.finish(group)
         if average and mult != 1.0:
             self.flat.mul_(mult)
+        elif not average and self.peer is not None and _world(group) > 1:
+            self.flat.mul_(float(_world(group)))  # (the peer-memory kernel averages in place)
