@@ -1,12 +1,14 @@
 """Data parallelism of the hot path: rays are independent, so each rank processes its own contiguous slice of the
-global batch with replicated parameters, and the only exchange is the all-reduce of a flat gradient arena
-(hash tables + MLP weights) per step.  Replaces the reference's DistributedDataParallel wrap with
-find_unused_parameters=True and 25 MiB buckets (nerfstudio/pipelines/base_pipeline.py:305-307): same result
-(sum / world_size), NCCL calls that NVSwitch can reduce in-network (NVLS).
+global batch with replicated parameters, and the only exchange is the average of a flat gradient arena (hash tables + MLP
+weights) per step.  Replaces the reference's DistributedDataParallel wrap with find_unused_parameters=True and 25 MiB
+buckets (nerfstudio/pipelines/base_pipeline.py:305-307): same result (sum / world_size).
+
+On one box the arena lives in symmetric memory and the collective is this package's kernel over NVLink peer memory
+(csrc/peer_reduce.cu: two-shot, reduction inside the NVSwitch when multicast is available, average fused); otherwise NCCL.
 
 The arena is reduced in two pieces so that the collective hides behind compute: the main hash table's gradient (64 MiB
 of the 88 MiB at BASELINE config 2 / 3) is final as soon as the field's backward kernels are enqueued - autograd runs
-them BEFORE the two proposal rounds' backward - so its all-reduce starts right there on a communication stream and
+them BEFORE the two proposal rounds' backward - so its reduction starts right there on a communication stream and
 overlaps with the proposal backward; only the small remainder (proposal table + MLPs) is reduced after the last kernel.
 """
 from __future__ import annotations
