@@ -18,7 +18,7 @@ from torch import Tensor
 
 from . import _lib
 from ._lib import AdamCfg, ptr, stream_ptr
-from .dist import OverlappedReduce, order_early_first
+from .dist import OverlappedReduce, order_early_first, peer_memory_or_none
 
 import ctypes as C
 
@@ -39,11 +39,12 @@ class _FlatGroup:
                 n_early = total
         self.params, self.offsets, self.numel = params, offsets, total
         self.p = torch.zeros((total,), device=dev, dtype=torch.float32)
-        self.g = torch.zeros_like(self.p)
+        self.peer = peer_memory_or_none(total, dev)  # data-parallel on one box: gradients in symmetric memory (dist.py)
+        self.g = self.peer.flat if self.peer is not None else torch.zeros_like(self.p)
         self.m = torch.zeros_like(self.p)
         self.v = torch.ones_like(self.p)  # padding lanes keep v = 1 so that eps = 0 cannot make them 0 / 0
         self.skipped = torch.zeros((1,), device=dev, dtype=torch.float32)  # steps GradScaler skipped (found_inf)
-        self.reducer = OverlappedReduce(self.g, n_early)
+        self.reducer = OverlappedReduce(self.g, n_early, self.peer)
         for i, (p, off) in enumerate(zip(params, offsets)):
             self.v[off : off + p.numel()].zero_()
             view = self.p[off : off + p.numel()].view_as(p)
