@@ -300,6 +300,10 @@ int nrb_alpha_composite_bwd(const float* alphas, const float* feats, const nrb_i
                             const float* ddepth, const float* daccumulation, float* dalphas, float* dfeats,
                             nrb_stream_t stream);
 
+/* render_depth_simple for given weights (models/neurad.py:721-728; `renderer_depth(prop_w, prop_rs)` of the proposal rounds,
+ * models/neuradar.py:528): depth [N] = sum_s weights[n,s] (start + end) / 2, and d depth / d weights. */
+int nrb_weighted_depth_fwd(const float* weights, const nrb_intervals_t* iv, int64_t N, float* depth, nrb_stream_t stream);
+int nrb_weighted_depth_bwd(const nrb_intervals_t* iv, const float* ddepth, int64_t N, float* dweights, nrb_stream_t stream);
 /* nerfacc.accumulate_along_rays on dense samples (call sites models/neurad.py:728, renderers.py:85,349,412):
  * out [N,C] = sum_s weights[N,S] * values[N,S,C]; values == NULL gives out [N] = sum_s weights. */
 int nrb_accumulate_fwd(const float* weights, const float* values, int64_t N, int32_t S, int32_t C, float* out,

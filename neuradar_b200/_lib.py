@@ -132,6 +132,8 @@ SIGNATURES = {
     "nrb_mlp_fwd": [C.POINTER(Mlp), _P, _P, _P, _I64, _P],
     "nrb_mlp_bwd": [C.POINTER(Mlp), _P, _P, _P, _P, C.POINTER(MlpGrad), _I64, _P],
     "nrb_sh16": [_P, _P, _I64, _I32, _P],
+    "nrb_weighted_depth_fwd": [_P, C.POINTER(Intervals), _I64, _P, _P],
+    "nrb_weighted_depth_bwd": [C.POINTER(Intervals), _P, _I64, _P, _P],
     "nrb_peer_all_reduce": [_P, _P, C.c_uint64, _I32, _I32, _I32, _I64, _I64, _F, _I32, _P],
     "nrb_radar_rays": [_P, _P, _P, _P, _P, _P, _P, _P, _I32, _I64, _P, _P, _P, _P, _P, _P, _P],
     "nrb_tc_linear": [_P, _P, _P, _I32, _I32, _I32, _I64, _P, _P],

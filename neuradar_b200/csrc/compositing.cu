@@ -300,9 +300,55 @@ __global__ void __launch_bounds__(256) accumulate_bwd_kernel(const float* __rest
   if (dw != nullptr) dw[gid] = dot;
 }
 
+// render_depth_simple (nerfstudio/models/neurad.py:721-728) for given weights: depth[n] = sum_s w[n,s] (start + end) / 2,
+// and its derivative with respect to the weights.  The midpoints are formed in registers from the bin edges.
+__global__ void __launch_bounds__(kRayWarps * 32) weighted_depth_fwd_kernel(const float* __restrict__ w, nrb_intervals_t iv,
+                                                                            int64_t N, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t n = static_cast<int64_t>(blockIdx.x) * kRayWarps + (threadIdx.x >> 5);
+  if (n >= N) return;
+  const int S = iv.num_samples;
+  const float* st = iv.starts + n * iv.row_stride;
+  const float* en = iv.ends + n * iv.row_stride;
+  float s = 0.0f;
+  for (int i = lane; i < S; i += 32) s += w[n * S + i] * ((st[i] + en[i]) / 2.0f);
+  s = warp_sum(s);
+  if (lane == 0) out[n] = s;
+}
+
+__global__ void __launch_bounds__(256) weighted_depth_bwd_kernel(nrb_intervals_t iv, const float* __restrict__ dout,
+                                                                 int64_t total, float* __restrict__ dw) {
+  const int64_t gid = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const int S = iv.num_samples;
+  const int64_t n = gid / S;
+  const int i = static_cast<int>(gid - n * S);
+  dw[gid] = dout[n] * ((iv.starts[n * iv.row_stride + i] + iv.ends[n * iv.row_stride + i]) / 2.0f);
+}
+
 }  // namespace nrb
 
 using namespace nrb;
+
+extern "C" int nrb_weighted_depth_fwd(const float* weights, const nrb_intervals_t* iv, int64_t N, float* depth,
+                                      nrb_stream_t stream) {
+  if (int rc = check_intervals("nrb_weighted_depth_fwd", iv)) return rc;
+  NRB_REQUIRE(weights && depth && N >= 0, NRB_ERR_BAD_ARG, "nrb_weighted_depth_fwd: null pointer");
+  if (N == 0) return NRB_OK;
+  weighted_depth_fwd_kernel<<<blocks_for(N, kRayWarps), kRayWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(weights, *iv, N,
+                                                                                                             depth);
+  return finish_launch("nrb_weighted_depth_fwd");
+}
+
+extern "C" int nrb_weighted_depth_bwd(const nrb_intervals_t* iv, const float* ddepth, int64_t N, float* dweights,
+                                      nrb_stream_t stream) {
+  if (int rc = check_intervals("nrb_weighted_depth_bwd", iv)) return rc;
+  NRB_REQUIRE(ddepth && dweights && N >= 0, NRB_ERR_BAD_ARG, "nrb_weighted_depth_bwd: null pointer");
+  if (N == 0) return NRB_OK;
+  const int64_t total = N * iv->num_samples;
+  weighted_depth_bwd_kernel<<<blocks_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(*iv, ddepth, total, dweights);
+  return finish_launch("nrb_weighted_depth_bwd");
+}
 
 extern "C" int nrb_accumulate_fwd(const float* weights, const float* values, int64_t N, int32_t S, int32_t C,
                                   float* out, nrb_stream_t stream) {

@@ -809,6 +809,33 @@ class _Accumulate(torch.autograd.Function):
         return dw, dv
 
 
+class _WeightedDepth(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, weights, iv: SampleIntervals):
+        w = f32c(weights)
+        N = w.shape[0]
+        out = torch.empty((N, 1), device=w.device, dtype=torch.float32)
+        i = iv.struct()
+        _lib.call("nrb_weighted_depth_fwd", ptr(w), C.byref(i), N, ptr(out), stream_ptr())
+        ctx.iv, ctx.shape = iv, w.shape
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, dout):
+        dout = f32c(dout)
+        dw = torch.empty(ctx.shape, device=dout.device, dtype=torch.float32)
+        i = ctx.iv.struct()
+        _lib.call("nrb_weighted_depth_bwd", C.byref(i), ptr(dout), ctx.shape[0], ptr(dw), stream_ptr())
+        return dw, None
+
+
+def weighted_depth(weights: Tensor, iv: SampleIntervals) -> Tensor:
+    """render_depth_simple (models/neurad.py:721-728): sum_s weights[N,S] (start + end) / 2 -> [N,1], midpoints in-kernel."""
+    return _WeightedDepth.apply(weights, iv)
+
+
 def accumulate(weights: Tensor, values: Optional[Tensor]) -> Tensor:
     """sum_s weights[N,S] * values[N,S,C] -> [N,C]  (values None -> [N,1])."""
     return _Accumulate.apply(weights, values)

@@ -187,8 +187,7 @@ class NeuRadarHotPath(nn.Module):
         carve = self.training and calc_lidar_losses and "is_lidar" in md and "directions_norm" in md
         lc = self.config.loss
         for i, (prop_w, prop_rs) in enumerate(zip(proposal_weights, proposal_ray_samples)):
-            steps = (prop_rs.frustums.starts + prop_rs.frustums.ends) / 2
-            nff_outputs[f"prop_depth_{i}"] = F.accumulate(prop_w[..., 0], steps)
+            nff_outputs[f"prop_depth_{i}"] = F.weighted_depth(prop_w[..., 0], prop_rs.intervals())
             if carve:  # carving loss of the proposal rounds (:529-531): sum((w * (is_lidar & ~is_close_to_lidar))^2)
                 nff_outputs[f"prop_weights_loss_{i}"] = F.carving_loss(
                     prop_w[..., 0], prop_rs.intervals(), md["is_lidar"], md["directions_norm"], md.get("did_return"),

@@ -143,3 +143,23 @@ def test_nff_outputs_training_extras():
     assert float(model.field.hashgrid.static_grid.hash_table.grad.abs().sum()) > 0
     heads = model.point_heads(rb, out["depth"].detach())
     assert heads["points"].shape == (n, 3) and heads["radar_xyz"].shape[0] == int(rays["is_radar"].sum())
+
+
+@pytest.mark.parametrize("n,S", [(1, 48), (300, 64), (77, 33)])
+def test_weighted_depth_forward_backward(n, S):
+    """render_depth_simple (models/neurad.py:721-728) with the midpoints formed in-kernel, against torch."""
+    from neuradar_b200 import functional as Fn
+
+    g = torch.Generator().manual_seed(n + S)
+    bins = torch.cumsum(torch.rand((n, S + 1), generator=g) + 0.01, dim=-1)
+    w = torch.rand((n, S), generator=g)
+    go = torch.randn((n, 1), generator=g)
+    wr = w.clone().requires_grad_(True)
+    ref = (wr * (bins[:, :-1] + bins[:, 1:]) / 2).sum(-1, keepdim=True)
+    (ref * go).sum().backward()
+    wd = w.to(DEV).requires_grad_(True)
+    out = Fn.weighted_depth(wd, Fn.SampleIntervals.from_bins(bins.to(DEV)))
+    assert out.shape == (n, 1)
+    assert rel_err(out, ref) <= 1e-6
+    (out * go.to(DEV)).sum().backward()
+    assert rel_err(wd.grad, wr.grad) <= 1e-6
