@@ -158,3 +158,24 @@ def test_shard_bounds_cover_the_batch():
     assert shard_bounds(10 * 1024, 4, 3, granule=1024) == (8192, 10240)
     with pytest.raises(ValueError):
         shard_bounds(1000, 2, 0, granule=256)
+
+
+def test_radar_fov_grid_sizes_match_torch_arange():
+    """Host arithmetic of the radar ray generator: rays per scan = len(torch.arange(min, max, step)) along each axis, also
+    where (max - min) / step lands within rounding of an integer in fp32."""
+    import types
+
+    from neuradar_b200.radars import fov_grid_sizes
+
+    g = torch.Generator().manual_seed(0)
+    n = 64
+    lo = -torch.rand((n, 1), generator=g)
+    step = torch.rand((n, 1), generator=g) * 0.1 + 0.01
+    k = torch.randint(3, 40, (n, 1), generator=g).float()
+    hi = lo + step * k + (torch.rand((n, 1), generator=g) - 0.5) * 1e-7  # straddles exact multiples
+    sensor = types.SimpleNamespace(min_azimuth=lo, max_azimuth=hi, radar_azimuth_ray_divergence=step,
+                                   min_elevation=lo * 0.5, max_elevation=hi * 0.5, radar_elevation_ray_divergence=step)
+    grid = fov_grid_sizes(sensor)
+    for i in range(n):
+        assert int(grid["n_az"][i]) == torch.arange(float(lo[i]), float(hi[i]), float(step[i])).numel(), i
+        assert int(grid["n_el"][i]) == torch.arange(float(lo[i] * 0.5), float(hi[i] * 0.5), float(step[i])).numel(), i
