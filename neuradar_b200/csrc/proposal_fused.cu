@@ -109,7 +109,9 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_fwd_kernel(
   }
 }
 
-template <int F>
+// kChunks = ceil(S / 32) rounded up to 2 / 4 / 8: the per-chunk state of the two scans lives in registers, and a kernel
+// instantiated for 8 chunks carries 40 of them for nothing at S <= 64 (90 registers and 5 blocks per SM instead of 8).
+template <int F, int kChunks>
 __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     const __grid_constant__ PropGrid g, const __grid_constant__ BwdPlan plan, const float* __restrict__ origins, const float* __restrict__ directions,
     const float* __restrict__ pixel_area, float scale, nrb_intervals_t iv, int64_t N,
@@ -134,10 +136,10 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     const float* en = iv.ends + n * iv.row_stride;
     const uint32_t mask = (1u << g.log2_size) - 1u;
     // forward recompute of the weight scan from the saved pre-activations
-    float delta[kMaxChunks], dd[kMaxChunks], trans[kMaxChunks], pre[kMaxChunks], gdens[kMaxChunks];
+    float delta[kChunks], dd[kChunks], trans[kChunks], pre[kChunks], gdens[kChunks];
     float carry = 0.0f;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       if (c * 32 < S) {
         const int i = c * 32 + lane;
         const bool ok = i < S;
@@ -154,7 +156,7 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
     // d weights -> d density (reverse exclusive scan), see density_weights_bwd_kernel
     float suffix = 0.0f;
 #pragma unroll
-    for (int c = kMaxChunks - 1; c >= 0; --c) {
+    for (int c = kChunks - 1; c >= 0; --c) {
       if (c * 32 < S) {
         const int i = c * 32 + lane;
         const bool ok = i < S;
@@ -178,12 +180,9 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
       }
     }
     // d density -> d pre (trunc_exp) -> decoder and table gradients
-    float ddec[NRB_MAX_LEVELS * F];
-#pragma unroll
-    for (int q = 0; q < NRB_MAX_LEVELS * F; ++q) ddec[q] = 0.0f;
     const unsigned spread = static_cast<unsigned>(blockIdx.x * kPropWarps + (threadIdx.x >> 5));
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < kChunks; ++c) {
       if (c * 32 < S) {  // warp-uniform: all lanes take part in the run merging below
         const int i = c * 32 + lane;
         const bool act = i < S;
@@ -212,36 +211,30 @@ __global__ void __launch_bounds__(kPropWarps * 32) proposal_bwd_kernel(
           }
         }
         const bool act_static = act && agid < 0;
+        // A real loop over the levels: unrolled 16 x (with the chunks: up to 128 copies of the merge-and-scatter body)
+        // the kernel was 150 K instructions, far beyond the instruction cache.
+#pragma unroll 1
+        for (int l = 0; l < g.num_levels; ++l) {
+          const float scal = g.scalings[l];
+          const Cell cell = locate_cell(q.x, q.y, q.z, scal, mask);
+          const float lw = level_weight(scal, q.std);
+          float gr[F];
 #pragma unroll
-        for (int l = 0; l < NRB_MAX_LEVELS; ++l) {
-          if (l < g.num_levels) {
-            const float scal = g.scalings[l];
-            const Cell cell = locate_cell(q.x, q.y, q.z, scal, mask);
-            const float lw = level_weight(scal, q.std);
-            float gr[F];
-#pragma unroll
-            for (int j = 0; j < F; ++j) {
-              ddec[l * F + j] = fmaf(gpre, sf[l * F + j], ddec[l * F + j]);
-              gr[j] = gpre * s_dec[l * F + j] * lw;
-            }
-            float w8[8];
-            corner_weights(cell, w8);
-            // runs of adjacent samples of the ray that share a cell are summed before scattering (hash_bwd_plan.cuh)
-            float v[8][F];
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-#pragma unroll
-              for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
-            merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act_static, lane, dtable, spread);
+          for (int j = 0; j < F; ++j) {
+            const float dd_lj = warp_sum(gpre * sf[l * F + j]);  // decoder gradient of this chunk's 32 samples
+            if (lane == 0) atomicAdd(&s_ddec[l * F + j], dd_lj);
+            gr[j] = gpre * s_dec[l * F + j] * lw;
           }
-        }
-      }
-    }
+          float w8[8];
+          corner_weights(cell, w8);
+          // runs of adjacent samples of the ray that share a cell are summed before scattering (hash_bwd_plan.cuh)
+          float v[8][F];
 #pragma unroll
-    for (int q = 0; q < NRB_MAX_LEVELS * F; ++q) {
-      if (q < LF) {
-        const float s = warp_sum(ddec[q]);
-        if (lane == 0) atomicAdd(&s_ddec[q], s);
+          for (int k = 0; k < 8; ++k)
+#pragma unroll
+            for (int j = 0; j < F; ++j) v[k][j] = w8[k] * gr[j];
+          merge_runs_and_scatter<F>(plan, l, g.log2_size, q.x, q.y, q.z, scal, cell, v, act_static, lane, dtable, spread);
+        }
       }
     }
   }
@@ -338,16 +331,25 @@ extern "C" int nrb_proposal_bwd(const nrb_rays_t* rays, const nrb_grid_t* grid, 
   BwdPlan plan;
   int64_t vertices = 0;
   if (int rc = prepare_bwd_plan(grid, N * iv->num_samples, workspace, workspace_bytes, s, &plan, &vertices)) return rc;
-#define NRB_LAUNCH(F)                                                                                              \
-  proposal_bwd_kernel<F><<<blocks, kPropWarps * 32, 0, s>>>(g, plan, rays->origins, rays->directions, rays->pixel_area,  \
-                                                            static_scale, *iv, N, saved_feats, saved_pre,          \
-                                                            dweights, ddensity, dtable, ddecoder_w)
+#define NRB_LAUNCH_C(F, CH)                                                                                        \
+  proposal_bwd_kernel<F, CH><<<blocks, kPropWarps * 32, 0, s>>>(g, plan, rays->origins, rays->directions,          \
+                                                                rays->pixel_area, static_scale, *iv, N, saved_feats, \
+                                                                saved_pre, dweights, ddensity, dtable, ddecoder_w)
+#define NRB_LAUNCH(F)                                   \
+  if (iv->num_samples <= 64) {                          \
+    NRB_LAUNCH_C(F, 2);                                 \
+  } else if (iv->num_samples <= 128) {                  \
+    NRB_LAUNCH_C(F, 4);                                 \
+  } else {                                              \
+    NRB_LAUNCH_C(F, kMaxChunks);                        \
+  }
   switch (grid->features_per_level) {
     case 1: NRB_LAUNCH(1); break;
     case 2: NRB_LAUNCH(2); break;
     default: NRB_LAUNCH(4); break;
   }
 #undef NRB_LAUNCH
+#undef NRB_LAUNCH_C
   switch (grid->features_per_level) {
     case 1: launch_fold<1>(grid, plan, dtable, vertices, s); break;
     case 2: launch_fold<2>(grid, plan, dtable, vertices, s); break;
