@@ -181,6 +181,16 @@ def grad_sink_of(table: Optional[Tensor]) -> Optional[Tensor]:
     return sink
 
 
+_CONSUMER_STREAMS = {}
+
+
+def note_consumer_stream(device) -> None:
+    """Called where a branch of the forward is moved to a side stream: the current stream is the one the training loop
+    runs on, i.e. the one that will read the gradient sinks after `backward()`."""
+    device = torch.device(device)
+    _CONSUMER_STREAMS[device] = torch.cuda.current_stream(device)
+
+
 def _sink_written(table: Tensor) -> None:
     """Called by a backward that added straight into a gradient sink (no tensor is returned to autograd for it, so
     autograd's own stream bookkeeping does not cover the write).  (1) If the backward ran on a side stream - autograd
@@ -188,11 +198,19 @@ def _sink_written(table: Tensor) -> None:
     or optimiser step issued after `loss.backward()` cannot race with the scatter.  (2) The owner of the sink may have
     registered a callback (dist.OverlappedReduce.start_early) to start reducing this gradient right away."""
     dev = table.device
-    cur, main = torch.cuda.current_stream(dev), torch.cuda.default_stream(dev)
-    if cur != main and not torch.cuda.is_current_stream_capturing():  # (a graph capture orders its own streams)
-        ev = torch.cuda.Event()
-        ev.record(cur)
-        main.wait_event(ev)
+    cur = torch.cuda.current_stream(dev)
+    if not torch.cuda.is_current_stream_capturing():  # (a graph capture orders its own streams)
+        # the default stream and the stream the forward was issued from (`note_consumer_stream`): whoever reads the sink next
+        waiters = {torch.cuda.default_stream(dev)}
+        consumer = _CONSUMER_STREAMS.get(dev)
+        if consumer is not None:
+            waiters.add(consumer)
+        waiters.discard(cur)
+        if waiters:
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            for s in waiters:
+                s.wait_event(ev)
     ready = getattr(table, "_nrb_grad_ready", None)
     if ready is not None:
         ready()

@@ -181,6 +181,7 @@ class ProposalNetworkSampler(Sampler):
         if not (self.overlap_backward and torch.is_grad_enabled() and dev.type == "cuda") or _data_parallel():
             return fn()
         main = torch.cuda.current_stream(dev)
+        F.note_consumer_stream(dev)
         side = F.side_stream(dev, 2)
         side.wait_stream(main)
         with torch.cuda.stream(side):
