@@ -137,6 +137,8 @@ def _data_parallel() -> bool:
     `early`) then hides behind the proposal backward, which is worth more than overlapping the two backward branches."""
     import torch.distributed as dist
 
+    if os.environ.get("NRB_DP_SERIAL_BACKWARD", "1") == "0":  # experiment switch: overlap the branches under DP as well
+        return False
     return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
 
 
