@@ -179,3 +179,23 @@ def test_radar_fov_grid_sizes_match_torch_arange():
     for i in range(n):
         assert int(grid["n_az"][i]) == torch.arange(float(lo[i]), float(hi[i]), float(step[i])).numel(), i
         assert int(grid["n_el"][i]) == torch.arange(float(lo[i] * 0.5), float(hi[i] * 0.5), float(step[i])).numel(), i
+
+
+def test_workload_roofline_arithmetic_matches_the_survey():
+    """bytes / FLOPs per ray that bench.py divides by."""
+    from neuradar_b200.synthetic import WORKLOADS
+
+    assert abs(WORKLOADS[2].bytes_per_ray() - 142_780) <= 300          # 2 x 70 656 gather/scatter + ray I/O
+    assert WORKLOADS[1].bytes_per_ray() == WORKLOADS[2].bytes_per_ray() == WORKLOADS[3].bytes_per_ray()
+    assert abs(WORKLOADS[5].bytes_per_ray() - 70_832) <= 10            # inference: gathers + 176 B of ray I/O
+    assert abs(WORKLOADS[4].bytes_per_ray() - 356_000) <= 2_000        # 2 x 176 947 + I/O
+    assert WORKLOADS[2].mlp_flop_per_ray() == 3 * 11_328 * 48          # 1.63 MFLOP per ray, fwd + bwd
+
+
+def test_peer_memory_is_only_used_for_single_box_nccl_jobs():
+    from neuradar_b200.dist import order_early_first, peer_memory_or_none
+
+    assert peer_memory_or_none(1024, "cpu") is None                    # no process group, not a CUDA device
+    a, b, c = (torch.nn.Parameter(torch.zeros(2)) for _ in range(3))
+    ordered, n_first = order_early_first([a, b, c], [c])
+    assert ordered[0] is c and n_first == 1 and ordered[1:] == [a, b]
