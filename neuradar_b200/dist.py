@@ -92,13 +92,17 @@ def peer_memory_or_none(numel: int, device, group=None) -> Optional[PeerMemory]:
         return None
     if int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size())) != dist.get_world_size():
         return None  # more than one box: the ranks do not share an NVSwitch domain
+    pm = None
     try:
-        return PeerMemory(numel, device, group)
+        pm = PeerMemory(numel, device, group)
     except Exception as e:  # noqa: BLE001 - no peer mapping on this system: NCCL carries the collective
         import warnings
 
         warnings.warn(f"neuradar_b200: peer-memory all-reduce unavailable ({type(e).__name__}: {str(e)[:120]}); using NCCL")
-        return None
+    # every rank must take the same route: agree on the outcome
+    ok = torch.tensor([1 if pm is not None else 0], device=device, dtype=torch.int32)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    return pm if int(ok.item()) == 1 else None
 
 
 class OverlappedReduce:
